@@ -1,0 +1,107 @@
+/* tiktaalik_b200.h -- C ABI of libtiktaalik_b200.so, the B200 (sm_100a) drop-in for the
+ * f2py/Fortran layer under tiktaalik.matrices / tiktaalik.evolution.
+ *
+ * Every entry point replaces one subroutine of the reference's f2py module `dummy`
+ * (tiktaalik/f90wrap/matrices.f90, tiktaalik/f90wrap/qcd.f90; paths relative to the
+ * reference root).  Plain pointers and sizes only: host arrays for the small inputs
+ * (xi, Q2), CUDA device pointers for kernels and matrices, the caller's CUDA stream as
+ * void*.  All entry points return 0 on success and non-zero on failure;
+ * tkb_last_error() then holds a message (the reference has no error channel below
+ * Python: matrices.py:40-41,68,198).
+ *
+ * State model: like the reference's Fortran module state (matevo.f90:27-46) there is one
+ * implicit context per process, bound to the CUDA device that is current at the first
+ * tkb_make_kernels call.  Not thread-safe, like the reference.
+ *
+ * Device layouts (index semantics are the API, strides are free):
+ *   evolution matrices  M[xi][Q2][i][j]  row-major m x m tiles, m = nx (NS) or 2 nx (SG);
+ *                       logical element (i, j, xi, Q2) of the reference's M(i,j,xi,Q2)
+ *   kernel slices       K[xi][i][j]
+ *   apply               g[j][xi][s] (the caller's (m, nxi, S) C-contiguous array),
+ *                       out[xi][Q2][i][s]
+ */
+#ifndef TIKTAALIK_B200_H
+#define TIKTAALIK_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* matrix / kernel type codes */
+enum { TKB_VNS = 0, TKB_VSG = 1, TKB_ANS = 2, TKB_ASG = 3 };
+enum { TKB_VQQ = 0, TKB_VQG = 1, TKB_VGQ = 2, TKB_VGG = 3, TKB_AQQ = 4, TKB_AQG = 5, TKB_AGQ = 6, TKB_AGG = 7 };
+
+const char* tkb_last_error(void);
+int tkb_version(void);
+
+/* replaces make_kernels_wrap (f90wrap/matrices.f90:35-41 -> matevo.f90:64-80, 283-480).
+ * Assembles all LO and NLO kernel matrices for nx pixels and nxi skewness values.  Like
+ * initialize_2D (matevo.f90:688-689) it clamps xi[0] >= 1e-6 and xi[nxi-1] <= 0.999999.
+ * Frees any evolution matrices. */
+int tkb_make_kernels(int nx, int nxi, const double* xi_host, int grid_type, void* stream);
+
+/* same, for one rank's slice of a xi list that was clamped globally before sharding:
+ * clamp_first / clamp_last say whether this slice holds the global first / last xi. */
+int tkb_make_kernels_shard(int nx, int nxi, const double* xi_host, int grid_type,
+                           int clamp_first, int clamp_last, void* stream);
+
+/* replaces make_matrices_wrap (f90wrap/matrices.f90:43-53 -> matevo.f90:82-96, 485-673). */
+int tkb_make_matrices(int nq2, const double* q2_host, int nlo, void* stream);
+
+/* replace get_nx_wrap / get_nxi_wrap / get_nQ2_wrap (f90wrap/matrices.f90:58-71) */
+int tkb_get_nx(void);
+int tkb_get_nxi(void);
+int tkb_get_nq2(void);
+int tkb_get_lnlo(void);
+
+/* replace evomatrix_{vns,vsg,ans,asg}_wrap (f90wrap/matrices.f90:76-110 -> matevo.f90:246-278).
+ * tkb_evomatrix returns a zero-copy view (valid until the next make_kernels/make_matrices):
+ * shape = (m, m, nxi, nq2) and element strides for the logical indices (i, j, xi, Q2).
+ * tkb_evomatrix_copy writes a private copy in the same [xi][Q2][i][j] layout (f2py's
+ * intent(out) semantics: the caller may modify it). */
+int tkb_evomatrix(int type, int nstype, const double** dev_ptr, int64_t shape[4], int64_t strides[4]);
+int tkb_evomatrix_copy(int type, int nstype, double* dev_out, void* stream);
+
+/* replace evokernel_{v,a}{qq,qg,gq,gg}_wrap (f90wrap/matrices.f90:115-193 -> matevo.f90:124-241):
+ * dev_out[xi][i][j] = a K0 (+ a^2 K1), a = alpha_s(q2)/(2 pi); nstype in {1,-1,0} for the QQ types. */
+int tkb_evokernel(int type, double q2, int nfl, int nlo, int nstype, double* dev_out, void* stream);
+
+/* replaces pixelspace_wrap (f90wrap/matrices.f90:21-30) */
+int tkb_pixelspace(int nx, double xi, int grid_type, double* host_out);
+
+/* replaces alpha_wrap (f90wrap/qcd.f90:19-29 -> alpha_qcd.f90:22-50) */
+int tkb_alpha(int n, const double* q2_host, double* out_host);
+
+/* replaces np.einsum('ijkl,jk...->ik...l', M, g) (evolution.py:259-348,507-509):
+ * out[xi][Q2][i][s] = sum_j M[xi][Q2][i][j] g[j][xi][s]; ldg = row stride of g in elements
+ * (nxi*S for a contiguous (m, nxi, S) array). */
+int tkb_apply(int m, int nxi, int nq2, int64_t S, const double* M_dev, const double* g_dev, int64_t ldg,
+              double* out_dev, void* stream);
+
+/* releases every device buffer of the implicit context */
+int tkb_free(void);
+
+/* ---- diagnostics used by the parity tests and the benchmark ---- */
+/* device pointers to the QAGS bookkeeping of the last tkb_make_kernels:
+ * arrays [xi][i][c][sub], c = 0 NSp, 1 NSm, 2 NS_nfl, 3 VGG, 4 AGG, 5 VGG_nfl, 6 AGG_nfl; sub = 0..2 */
+int tkb_qags_info(const double** res_dev, const int** last_dev, const int** ifail_dev);
+/* composed nfl slice, row-major per xi: which = 0 K_NS_0, 1 KV_NS_1p, 2 KV_NS_1m (n x n),
+ * 3 KV_SG_0, 4 KA_SG_0, 5 KV_SG_1, 6 KA_SG_1 (2n x 2n) */
+int tkb_raw_kernel(int which, int nfl, const double** dev_ptr, void* stream);
+/* all 22 two-variable kernels at npts points: out[p][22] */
+int tkb_eval_kernels(int npts, const double* x_dev, const double* y_dev, const double* xi_dev, double* out_dev,
+                     void* stream);
+/* which = 0 log(a), 1 pow(a,b), 2 dilog(a) with the library's own device arithmetic */
+int tkb_eval_scalar(int which, int npts, const double* a_dev, const double* b_dev, double* out_dev, void* stream);
+/* device time in ms of the stages of the last tkb_make_kernels / tkb_make_matrices:
+ * ms[0] fixed quadrature, ms[1] QAGS constants, ms[2] RK4 stepping (incl. composition) */
+int tkb_stage_ms(double ms[3]);
+/* number of kernel launches issued by the library since load */
+long long tkb_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

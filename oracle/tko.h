@@ -93,6 +93,10 @@ double tko_interpixel(int n_pixels, int i, double x, double xi, int grid_type);
 void   tko_pixelspace(int nx, double xi, int grid_type, double *x);   /* f90wrap/matrices.f90:21-30 */
 double tko_grid_node(int i, int nx, double xi, int grid_type);       /* convolution.f90:45-46 */
 
+/* test hooks for the primitives of tko_fp.h */
+double tko_log_x(double x);
+double tko_pow_x(double x, double y);
+
 /* ---- integration.f90 ---- */
 void tko_qk21(tko_f1 f, void *ctx, double a, double b,
               double *result, double *abserr, double *resabs, double *resasc);

@@ -1,0 +1,848 @@
+// assemble.cu -- kernel-matrix assembly on sm_100a: K1 fixed Gauss-Kronrod quadrature,
+// K2 warp-cooperative QAGS for the NLO plus-prescription constants, K3 composition into the
+// nfl-dependent kernel matrices.  Compiled with -fmad=false (see tkb_fp.cuh).
+//
+// Reference path replaced (file:line):
+//   matevo.f90:283-480   make_kernels_NS_0 / NS_1 / SG_0 / SG_1  (24 pixel_conv per (xi,i,j))
+//   convolution.f90:26-97 pixel_conv = reg + pls + cst
+//   integration.f90:18-49 integrate = 6 x qk21 (126 fixed nodes), :51-64 adaptive_integrate = 3 x qags
+//   kernels_nlo.f90:60-78 ... 925-944  the eight *_cst functions
+//
+// Design (differs from the reference on purpose):
+//   * the integrand factorises over the column j: for fixed (xi, i) the 126 nodes y_k and all
+//     22 kernel values K_f(x_i, y_k, xi) do not depend on j, only the basis value f_j(y_k) does,
+//     and it is non-zero for 6 consecutive j.  K1 evaluates every kernel ONCE per node
+//     (one thread per (node, half), shared transcendental values, tkb_kernels.cuh) and then
+//     replays qk21's accumulation per column from shared memory.  Per-term values and the
+//     summation order are those of the reference, so entries agree bit for bit with a
+//     straight evaluation, at 1/nx of the kernel evaluations.
+//   * K2 runs one QAGS instance per warp: the 2 x 21 nodes of a bisection step are 168
+//     half-kernel tasks spread over the lanes; the scalar QUADPACK bookkeeping (qsort, qextr)
+//     runs on lane 0 on per-warp interval lists.  Control flow is QUADPACK's, comparison for
+//     comparison, so the bisection path is the reference's.
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "tkb_fp.cuh"
+#include "tkb_kernels.cuh"
+#include "tkb_grid.cuh"
+#include "tkb_internal.h"
+
+namespace tkb {
+
+// Gauss-Kronrod 21 abscissae / weights (integration.f90:139-152), 1-based like the reference
+__constant__ double c_xgk[12] = { 0.0,
+    9.956571630258081e-01, 9.739065285171717e-01, 9.301574913557082e-01, 8.650633666889845e-01,
+    7.808177265864169e-01, 6.794095682990244e-01, 5.627571346686047e-01, 4.333953941292472e-01,
+    2.943928627014602e-01, 1.488743389816312e-01, 0.000000000000000 };
+__constant__ double c_wgk[12] = { 0.0,
+    1.169463886737187e-02, 3.255816230796473e-02, 5.475589657435200e-02, 7.503967481091995e-02,
+    9.312545458369761e-02, 1.093871588022976e-01, 1.234919762620659e-01, 1.347092173114733e-01,
+    1.427759385770601e-01, 1.477391049013385e-01, 1.494455540029169e-01 };
+__constant__ double c_wg[6] = { 0.0,
+    6.667134430868814e-02, 1.494513491505806e-01, 2.190863625159820e-01, 2.692667193099964e-01,
+    2.955242247147529e-01 };
+
+// plus-type kernels: integrand K (f_j(y) - f_j(x)); the rest are regular: K f_j(y)
+__host__ __device__ constexpr bool is_plus(int k)
+{
+    return k == K_K0QQ || k == K_A0GG || k == K_NSP || k == K_NSM || k == K_NSN ||
+           k == K_V1GG || k == K_A1GG || k == K_V1GGN || k == K_A1GGN;
+}
+
+// position q (0..20) in the per-interval node table -> eta.  q = 0 centre; q = 2t-1 / 2t are
+// centr -/+ hlgth*xgk(t), t = 1..10 (qk21, integration.f90:174-203)
+TKB_DEV double node_eta(double centr, double hlgth, int q)
+{
+    if (q == 0) return centr;
+    const int t = (q + 1) >> 1;
+    const double absc = hlgth * c_xgk[t];
+    return (q & 1) ? (centr - absc) : (centr + absc);
+}
+
+// ---------------------------------------------------------------------------------------
+// K1: fixed quadrature.  grid = (n, nxi), block = 256 threads.
+// P layout: P[f][ixi][i][j] (row-major n x n per xi).  diag layout: diag[ixi][i][DIAG_N].
+
+constexpr int K1_THREADS = 256;
+constexpr int NNODE = 126;
+
+__global__ void __launch_bounds__(K1_THREADS)
+assemble_fixed_kernel(int n, int nxi, const double* __restrict__ xi_arr, int grid_type,
+                      double* __restrict__ P, double* __restrict__ diag)
+{
+    __shared__ double s_K[NKERN][NNODE];      // kernel values at the nodes
+    __shared__ double s_J[NNODE];             // Jacobians
+    __shared__ double s_b[NNODE][6];          // basis rows at the nodes
+    __shared__ int s_iS[NNODE];               // stencil origins (1-based)
+    __shared__ double s_aa[8], s_hl[6], s_w[6], s_bx[6];
+    __shared__ int s_iSx;
+    __shared__ int s_allfinite;
+
+    const int i = blockIdx.x + 1;             // 1-based row
+    const int ixi = blockIdx.y;
+    const int tid = threadIdx.x;
+    const double xi = xi_arr[ixi];
+    const double x = grid_node(i, n, xi, grid_type);
+
+    if (tid == 0) {
+        // integration.f90:27-35: breakpoints in eta space, inner pairs sorted
+        double aa[8];
+        aa[1] = pull_back(-1.0, xi, grid_type);
+        aa[2] = pull_back(-fabs(x), xi, grid_type);
+        aa[3] = pull_back(-fabs(xi), xi, grid_type);
+        aa[4] = pull_back(0.0, xi, grid_type);
+        aa[5] = pull_back(fabs(xi), xi, grid_type);
+        aa[6] = pull_back(fabs(x), xi, grid_type);
+        aa[7] = pull_back(1.0, xi, grid_type);
+        if (aa[3] < aa[2]) { const double z = aa[2]; aa[2] = aa[3]; aa[3] = z; }
+        if (aa[6] < aa[5]) { const double z = aa[5]; aa[5] = aa[6]; aa[6] = z; }
+        for (int r = 1; r <= 7; r++) s_aa[r] = aa[r];
+        for (int r = 0; r < 6; r++) s_hl[r] = 5.0e-01 * (aa[r + 2] - aa[r + 1]);
+        double w[6];
+        lagrange_weights(n, w);
+        for (int m = 0; m < 6; m++) s_w[m] = w[m];
+        // basis row at x_i itself (interpixel(j, x): pull_back then Lagrange, convolution.f90:77,93)
+        double bx[6];
+        s_iSx = basis_row(pull_back(x, xi, grid_type), n, w, bx);
+        for (int m = 0; m < 6; m++) s_bx[m] = bx[m];
+        s_allfinite = 1;
+    }
+    __syncthreads();
+
+    // ---- phase 1: one thread per (node, half) ----
+    {
+        const int k = tid >> 1, half = tid & 1;
+        const bool active = k < NNODE;
+        double hv[NKERN];
+        double J = 1.0;
+        if (active) {
+            const int r = k / 21, q = k - 21 * r;
+            const double a = s_aa[r + 1], b = s_aa[r + 2];
+            const double centr = 5.0e-01 * (a + b);
+            const double hlgth = 5.0e-01 * (b - a);
+            const double eta = node_eta(centr, hlgth, q);
+            const double y = push_forward(eta, xi, grid_type);
+            if (half == 0) {
+                J = push_jacob(eta, xi, grid_type);
+                s_J[k] = J;
+            } else {
+                double w[6], bb[6];
+#pragma unroll
+                for (int m = 0; m < 6; m++) w[m] = s_w[m];
+                s_iS[k] = basis_row(pull_back(y, xi, grid_type), n, w, bb);
+#pragma unroll
+                for (int m = 0; m < 6; m++) s_b[k][m] = bb[m];
+            }
+            const double X1 = 0.5 * (1.0 + x / xi), X2 = 0.5 * (1.0 - x / xi);
+            const double Y1 = 0.5 * (1.0 + y / xi), Y2 = 0.5 * (1.0 - y / xi);
+            if (half == 0) eval_half<MASK_ALL>(X1, Y1, X2, Y2, hv);
+            else eval_half<MASK_ALL>(X2, Y2, X1, Y1, hv);
+        } else {
+#pragma unroll
+            for (int f = 0; f < NKERN; f++) hv[f] = 0.0;
+        }
+        bool fin = true;
+#pragma unroll
+        for (int f = 0; f < NKERN; f++) {
+            const double other = __shfl_xor_sync(0xffffffffu, hv[f], 1);
+            if (active && half == 0) {
+                const double K = combine_halves_rt(f, hv[f], other, xi);
+                s_K[f][k] = K;
+                fin = fin && (fabs(K) <= huge_());
+            }
+        }
+        if (active && half == 0 && !(fin && fabs(J) <= huge_())) s_allfinite = 0;
+    }
+    __syncthreads();
+
+    // ---- phase 2: one thread per column j; replay qk21 per interval in the reference's order ----
+    const bool dense = (s_allfinite == 0);     // a NaN/Inf kernel value poisons every column (0*NaN)
+    const int iSx = s_iSx;
+    const size_t rowbase = ((size_t)ixi * n + (size_t)(i - 1)) * n;
+    const size_t fstride = (size_t)nxi * n * n;
+    for (int j = tid + 1; j <= n; j += K1_THREADS) {
+        const int mx = j - iSx;
+        const double fx = (mx >= 0 && mx < 6) ? s_bx[mx] : 0.0;
+        double integral[NKERN];
+#pragma unroll
+        for (int f = 0; f < NKERN; f++) integral[f] = 0.0;
+        for (int r = 0; r < 6; r++) {
+            double resk[NKERN];
+#pragma unroll
+            for (int f = 0; f < NKERN; f++) resk[f] = 0.0;
+            // qk21 order: centre (weight wgk(11)), then t = 2,4,..,10, then t = 1,3,..,9
+            for (int s = 0; s <= 10; s++) {
+                const int t = (s == 0) ? 11 : ((s <= 5) ? 2 * s : 2 * (s - 5) - 1);
+                const int k1 = 21 * r + ((s == 0) ? 0 : 2 * t - 1);
+                const int k2 = k1 + 1;                       // unused for the centre
+                const int m1 = j - s_iS[k1];
+                const bool in1 = (m1 >= 0 && m1 < 6);
+                bool in2 = false;
+                int m2 = 0;
+                if (s != 0) { m2 = j - s_iS[k2]; in2 = (m2 >= 0 && m2 < 6); }
+                if (!(dense || in1 || in2 || fx != 0.0)) continue;
+                const double fy1 = in1 ? s_b[k1][m1] : 0.0;
+                const double J1 = s_J[k1];
+                const double w = c_wgk[t];
+                if (s == 0) {
+#pragma unroll
+                    for (int f = 0; f < NKERN; f++) {
+                        const double fc = is_plus(f) ? (s_K[f][k1] * (fy1 - fx)) * J1 : (s_K[f][k1] * fy1) * J1;
+                        resk[f] = w * fc;
+                    }
+                } else {
+                    const double fy2 = in2 ? s_b[k2][m2] : 0.0;
+                    const double J2 = s_J[k2];
+#pragma unroll
+                    for (int f = 0; f < NKERN; f++) {
+                        const double v1 = is_plus(f) ? (s_K[f][k1] * (fy1 - fx)) * J1 : (s_K[f][k1] * fy1) * J1;
+                        const double v2 = is_plus(f) ? (s_K[f][k2] * (fy2 - fx)) * J2 : (s_K[f][k2] * fy2) * J2;
+                        const double fsum = v1 + v2;
+                        resk[f] = resk[f] + w * fsum;
+                    }
+                }
+            }
+            const double hl = s_hl[r];
+#pragma unroll
+            for (int f = 0; f < NKERN; f++) integral[f] = integral[f] + resk[f] * hl;
+        }
+#pragma unroll
+        for (int f = 0; f < NKERN; f++) P[(size_t)f * fstride + rowbase + (size_t)(j - 1)] = integral[f];
+    }
+
+    // ---- diagonal bookkeeping: f_i(x_i) and the analytic LO constants ----
+    if (tid == 0) {
+        double* d = diag + ((size_t)ixi * n + (size_t)(i - 1)) * DIAG_N;
+        const int mi = i - iSx;
+        d[DIAG_FX] = (mi >= 0 && mi < 6) ? s_bx[mi] : 0.0;
+        d[DIAG_X] = x;
+        d[DIAG_K0QQ] = K0_qq_cst(x, xi);
+        d[DIAG_A0GG] = KA0_GG_cst(x, xi);
+        d[DIAG_A0GGN] = KA0_GG_nfl_cst();
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// K2: QAGS (integration.f90:246-904), one instance per warp.
+
+constexpr int QLIMIT = 500;
+
+struct QagsScratch {            // per-warp interval lists, 1-based like the reference
+    double alist[QLIMIT + 1], blist[QLIMIT + 1], rlist[QLIMIT + 1], elist[QLIMIT + 1];
+    double rlist2[53];
+    int iord[QLIMIT + 1];
+};
+
+size_t qags_scratch_bytes() { return sizeof(QagsScratch); }
+
+// integration.f90:616-729
+__device__ void qsort_(int limit, int last, int& maxerr, double& ermax, const double* elist, int* iord, int& nrmax)
+{
+    int i, ibeg, isucc, j, jbnd, jupbn, k;
+    double errmax, errmin;
+    if (last <= 2) {
+        iord[1] = 1;
+        iord[2] = 2;
+        goto L90;
+    }
+    errmax = elist[maxerr];
+    {
+        const int ntrip = nrmax - 1;
+        for (i = 1; i <= ntrip; i++) {
+            isucc = iord[nrmax - 1];
+            if (errmax <= elist[isucc]) break;
+            iord[nrmax] = isucc;
+            nrmax = nrmax - 1;
+        }
+    }
+    jupbn = last;
+    if (last > (limit / 2 + 2)) jupbn = limit + 3 - last;
+    errmin = elist[last];
+    jbnd = jupbn - 1;
+    ibeg = nrmax + 1;
+    for (i = ibeg; i <= jbnd; i++) {
+        isucc = iord[i];
+        if (errmax >= elist[isucc]) goto L60;
+        iord[i - 1] = isucc;
+    }
+    iord[jbnd] = maxerr;
+    iord[jupbn] = last;
+    goto L90;
+L60:
+    iord[i - 1] = maxerr;
+    k = jbnd;
+    for (j = i; j <= jbnd; j++) {
+        isucc = iord[k];
+        if (errmin < elist[isucc]) goto L80;
+        iord[k + 1] = isucc;
+        k = k - 1;
+    }
+    iord[i] = last;
+    goto L90;
+L80:
+    iord[k + 1] = last;
+L90:
+    maxerr = iord[nrmax];
+    ermax = elist[maxerr];
+}
+
+// integration.f90:732-904
+__device__ void qextr_(int& n, double* epstab, double& result, double& abserr, double* res3la, int& nres)
+{
+    int i, ib, ib2, ie, indx, k1, k2, k3, limexp, newelm, num;
+    double delta1, delta2, delta3, epsinf, error, err1, err2, err3, e0, e1, e1abs, e2, e3, res, ss, tol1, tol2, tol3;
+    nres = nres + 1;
+    abserr = huge_();
+    result = epstab[n];
+    if (n < 3) goto L100;
+    limexp = 50;
+    epstab[n + 2] = epstab[n];
+    newelm = (n - 1) / 2;
+    epstab[n] = huge_();
+    num = n;
+    k1 = n;
+    for (i = 1; i <= newelm; i++) {
+        k2 = k1 - 1;
+        k3 = k1 - 2;
+        res = epstab[k1 + 2];
+        e0 = epstab[k3];
+        e1 = epstab[k2];
+        e2 = res;
+        e1abs = fabs(e1);
+        delta2 = e2 - e1;
+        err2 = fabs(delta2);
+        tol2 = fmax2(fabs(e2), e1abs) * eps_();
+        delta3 = e1 - e0;
+        err3 = fabs(delta3);
+        tol3 = fmax2(e1abs, fabs(e0)) * eps_();
+        if (err2 <= tol2 && err3 <= tol3) {
+            result = res;
+            abserr = err2 + err3;
+            goto L100;
+        }
+        e3 = epstab[k1];
+        epstab[k1] = e1;
+        delta1 = e1 - e3;
+        err1 = fabs(delta1);
+        tol1 = fmax2(e1abs, fabs(e3)) * eps_();
+        if (err1 <= tol1 || err2 <= tol2 || err3 <= tol3) goto L20;
+        ss = 1.0 / delta1 + 1.0 / delta2 - 1.0 / delta3;
+        epsinf = fabs(ss * e1);
+        if (epsinf > 1.0e-04) goto L30;
+L20:
+        n = i + i - 1;
+        break;
+L30:
+        res = e1 + 1.0 / ss;
+        epstab[k1] = res;
+        k1 = k1 - 2;
+        error = err2 + fabs(res - e2) + err3;
+        if (error <= abserr) {
+            abserr = error;
+            result = res;
+        }
+    }
+    if (n == limexp) n = 2 * (limexp / 2) - 1;
+    if ((num / 2) * 2 == num) ib = 2; else ib = 1;
+    ie = newelm + 1;
+    for (i = 1; i <= ie; i++) {
+        ib2 = ib + 2;
+        epstab[ib] = epstab[ib2];
+        ib = ib2;
+    }
+    if (num != n) {
+        indx = num - n + 1;
+        for (i = 1; i <= n; i++) {
+            epstab[i] = epstab[indx];
+            indx = indx + 1;
+        }
+    }
+    if (nres < 4) {
+        res3la[nres] = result;
+        abserr = huge_();
+    } else {
+        abserr = fabs(result - res3la[3]) + fabs(result - res3la[2]) + fabs(result - res3la[1]);
+        res3la[1] = res3la[2];
+        res3la[2] = res3la[3];
+        res3la[3] = result;
+    }
+L100:
+    abserr = fmax2(abserr, 0.5 * eps_() * fabs(result));
+}
+
+// qk21's reductions from the 21 stored integrand values (integration.f90:159-222).
+// fv[q]: q = 0 centre, 2t-1 / 2t = value at centr -/+ hlgth*xgk(t).
+__device__ void qk21_reduce(const double* fv, double a, double b,
+                            double& result, double& abserr, double& resabs, double& resasc)
+{
+    const double hlgth = 5.0e-01 * (b - a);
+    const double dhlgth = fabs(hlgth);
+    double resg = 0.0;
+    const double fc = fv[0];
+    double resk = c_wgk[11] * fc;
+    resabs = fabs(resk);
+    for (int j = 1; j <= 5; j++) {
+        const int jtw = 2 * j;
+        const double fval1 = fv[2 * jtw - 1], fval2 = fv[2 * jtw];
+        const double fsum = fval1 + fval2;
+        resg = resg + c_wg[j] * fsum;
+        resk = resk + c_wgk[jtw] * fsum;
+        resabs = resabs + c_wgk[jtw] * (fabs(fval1) + fabs(fval2));
+    }
+    for (int j = 1; j <= 5; j++) {
+        const int jtwm1 = 2 * j - 1;
+        const double fval1 = fv[2 * jtwm1 - 1], fval2 = fv[2 * jtwm1];
+        const double fsum = fval1 + fval2;
+        resk = resk + c_wgk[jtwm1] * fsum;
+        resabs = resabs + c_wgk[jtwm1] * (fabs(fval1) + fabs(fval2));
+    }
+    const double reskh = resk * 5.0e-01;
+    resasc = c_wgk[11] * fabs(fc - reskh);
+    for (int j = 1; j <= 10; j++)
+        resasc = resasc + c_wgk[j] * (fabs(fv[2 * j - 1] - reskh) + fabs(fv[2 * j] - reskh));
+    result = resk * hlgth;
+    resabs = resabs * dhlgth;
+    resasc = resasc * dhlgth;
+    abserr = fabs((resk - resg) * hlgth);
+    if (resasc != 0.0 && abserr != 0.0)
+        abserr = resasc * fmin2(1.0, pow_(2.0e+02 * abserr / resasc, 1.5));
+    if (resabs > tiny_() / (5.0e+01 * eps_()))
+        abserr = fmax2((eps_() * 5.0e+01) * resabs, abserr);
+}
+
+// Warp-cooperative evaluation of the integrand K(x,y,xi) - K(y,x,xi) (kernels_nlo.f90:71-77) at
+// the 21 nodes of `nint` intervals (1 or 2).  4 tasks per node: (direction, half).
+template <int KID>
+__device__ __forceinline__ void eval_integrand_warp(double x, double xi, int nint,
+                                                    double a1, double b1, double a2, double b2,
+                                                    double* __restrict__ fv /* [42] shared */, int lane)
+{
+    const int ntask = 84 * nint;
+    for (int base = 0; base < ntask; base += 32) {
+        const int task = base + lane;
+        const bool active = task < ntask;
+        double hval = 0.0;
+        const int node = task >> 2, dir = (task >> 1) & 1, half = task & 1;
+        if (active) {
+            const int iv = node / 21, q = node - 21 * iv;
+            const double a = iv ? a2 : a1, b = iv ? b2 : b1;
+            const double centr = 5.0e-01 * (a + b);
+            const double hlgth = 5.0e-01 * (b - a);
+            const double y = node_eta(centr, hlgth, q);
+            const double u = dir ? y : x, v = dir ? x : y;         // K(u, v, xi)
+            const double X1 = 0.5 * (1.0 + u / xi), X2 = 0.5 * (1.0 - u / xi);
+            const double Y1 = 0.5 * (1.0 + v / xi), Y2 = 0.5 * (1.0 - v / xi);
+            double out[NKERN];
+            if (half == 0) eval_half<bit(KID)>(X1, Y1, X2, Y2, out);
+            else eval_half<bit(KID)>(X2, Y2, X1, Y1, out);
+            hval = out[KID];
+        }
+        const double h2 = __shfl_xor_sync(0xffffffffu, hval, 1);
+        double K = 0.0;
+        if (active && half == 0) K = combine_halves<KID>(hval, h2, xi);
+        const double Kyx = __shfl_xor_sync(0xffffffffu, K, 2);
+        if (active && half == 0 && dir == 0) fv[node] = K - Kyx;
+    }
+    __syncwarp();
+}
+
+struct QagsOut { double result, abserr; int last, ifail; };
+
+// One QAGS instance on one warp.  Lane 0 owns the scalar state.
+template <int KID>
+__device__ void qags_warp(double x, double xi, double a, double b, QagsScratch* __restrict__ S,
+                          double* __restrict__ fv, int lane, QagsOut& o)
+{
+    const double epsabs = 1.0e-12, epsrel = 1.0e-06;       // iqags defaults (integration.f90:238-239)
+    const int limit = QLIMIT;
+    bool extrap = false, noext = false;
+    int id, ierro = 0, iroff1 = 0, iroff2 = 0, iroff3 = 0, jupbnd, k, ksgn = 0, ktmin = 0, last = 0, maxerr = 1,
+        nres = 0, nrmax = 1, numrl2 = 2, ifail = 0;
+    double abseps, area = 0, area1, area12, area2, a1 = 0, a2 = 0, b1 = 0, b2 = 0, correc = 0, defabs, defab1, defab2,
+           dres, erlarg = 0, erlast, errbnd, errmax = 0, error1, error2, erro12, errsum = 0, ertest = 0, resabs,
+           reseps, res3la[4], small = 0, result = 0.0, abserr = 0.0;
+    double* alist = S->alist; double* blist = S->blist; double* rlist = S->rlist; double* elist = S->elist;
+    double* rlist2 = S->rlist2; int* iord = S->iord;
+    int status = 0;     // lane 0: 0 continue loop, 1 exit loop (Fortran `exit`), 2 goto 115, 3 goto 140 (early return)
+
+    // first approximation
+    eval_integrand_warp<KID>(x, xi, 1, a, b, a, b, fv, lane);
+    if (lane == 0) {
+        alist[1] = a; blist[1] = b; rlist[1] = 0.0; elist[1] = 0.0;
+        qk21_reduce(fv, a, b, result, abserr, defabs, resabs);
+        dres = fabs(result);
+        errbnd = fmax2(epsabs, epsrel * dres);
+        last = 1;
+        rlist[1] = result;
+        elist[1] = abserr;
+        iord[1] = 1;
+        if (abserr <= 1.0e+02 * eps_() * defabs && abserr > errbnd) ifail = 2;
+        if (limit == 1) ifail = 1;
+        if (ifail != 0 || (abserr <= errbnd && abserr != resabs) || abserr == 0.0) status = 3;
+        else {
+            rlist2[1] = result;
+            errmax = abserr;
+            maxerr = 1;
+            area = result;
+            errsum = abserr;
+            abserr = huge_();
+            if (dres >= (1.0 - 5.0e+01 * eps_()) * defabs) ksgn = 1; else ksgn = -1;
+        }
+    }
+    status = __shfl_sync(0xffffffffu, status, 0);
+    __syncwarp();
+
+    if (status != 3) {
+        for (last = 2; last <= limit; last++) {
+            if (lane == 0) {
+                a1 = alist[maxerr];
+                b1 = 5.0e-01 * (alist[maxerr] + blist[maxerr]);
+                a2 = b1;
+                b2 = blist[maxerr];
+                erlast = errmax;
+            }
+            a1 = __shfl_sync(0xffffffffu, a1, 0); b1 = __shfl_sync(0xffffffffu, b1, 0);
+            a2 = __shfl_sync(0xffffffffu, a2, 0); b2 = __shfl_sync(0xffffffffu, b2, 0);
+            eval_integrand_warp<KID>(x, xi, 2, a1, b1, a2, b2, fv, lane);
+            if (lane == 0) {
+                status = 0;
+                qk21_reduce(fv, a1, b1, area1, error1, resabs, defab1);
+                qk21_reduce(fv + 21, a2, b2, area2, error2, resabs, defab2);
+                area12 = area1 + area2;
+                erro12 = error1 + error2;
+                errsum = errsum + erro12 - errmax;
+                area = area + area12 - rlist[maxerr];
+                if (defab1 == error1 || defab2 == error2) goto L15;
+                if (fabs(rlist[maxerr] - area12) > (double)1.0e-05f * fabs(area12) || erro12 < 9.9e-01 * errmax) goto L10;
+                if (extrap) iroff2 = iroff2 + 1; else iroff1 = iroff1 + 1;
+L10:
+                if (last > 10 && erro12 > errmax) iroff3 = iroff3 + 1;
+L15:
+                rlist[maxerr] = area1;
+                rlist[last] = area2;
+                errbnd = fmax2(epsabs, epsrel * fabs(area));
+                if (iroff1 + iroff2 >= 10 || iroff3 >= 20) ifail = 2;
+                if (iroff2 >= 5) ierro = 3;
+                if (last == limit) ifail = 1;
+                if (fmax2(fabs(a1), fabs(b2)) <= (1.0 + 1.0e+03 * eps_()) * (fabs(a2) + 1.0e+03 * tiny_())) ifail = 4;
+                if (error2 <= error1) {
+                    alist[last] = a2;
+                    blist[maxerr] = b1;
+                    blist[last] = b2;
+                    elist[maxerr] = error1;
+                    elist[last] = error2;
+                } else {
+                    alist[maxerr] = a2;
+                    alist[last] = a1;
+                    blist[last] = b1;
+                    rlist[maxerr] = area2;
+                    rlist[last] = area1;
+                    elist[maxerr] = error2;
+                    elist[last] = error1;
+                }
+                qsort_(limit, last, maxerr, errmax, elist, iord, nrmax);
+                if (errsum <= errbnd) { status = 2; goto Lend; }
+                if (ifail != 0) { status = 1; goto Lend; }
+                if (last == 2) goto L80;
+                if (noext) goto Lend;
+                erlarg = erlarg - erlast;
+                if (fabs(b1 - a1) > small) erlarg = erlarg + erro12;
+                if (extrap) goto L40;
+                if (fabs(blist[maxerr] - alist[maxerr]) > small) goto Lend;
+                extrap = true;
+                nrmax = 2;
+L40:
+                if (ierro != 3 && erlarg > ertest) {
+                    id = nrmax;
+                    jupbnd = last;
+                    if (last > (2 + limit / 2)) jupbnd = limit + 3 - last;
+                    for (k = id; k <= jupbnd; k++) {
+                        maxerr = iord[nrmax];
+                        errmax = elist[maxerr];
+                        if (fabs(blist[maxerr] - alist[maxerr]) > small) goto Lend;
+                        nrmax = nrmax + 1;
+                    }
+                }
+                numrl2 = numrl2 + 1;
+                rlist2[numrl2] = area;
+                qextr_(numrl2, rlist2, reseps, abseps, res3la, nres);
+                ktmin = ktmin + 1;
+                if (ktmin > 5 && abserr < 1.0e-03 * errsum) ifail = 5;
+                if (abseps < abserr) {
+                    ktmin = 0;
+                    abserr = abseps;
+                    result = reseps;
+                    correc = erlarg;
+                    ertest = fmax2(epsabs, epsrel * fabs(reseps));
+                    if (abserr <= ertest) { status = 1; goto Lend; }
+                }
+                if (numrl2 == 1) noext = true;
+                if (ifail == 5) { status = 1; goto Lend; }
+                maxerr = iord[1];
+                errmax = elist[maxerr];
+                nrmax = 1;
+                extrap = false;
+                small = small * 5.0e-01;
+                erlarg = errsum;
+                goto Lend;
+L80:
+                small = fabs(b - a) * 3.75e-01;
+                erlarg = errsum;
+                ertest = errbnd;
+                rlist2[2] = area;
+Lend:
+                ;
+            }
+            status = __shfl_sync(0xffffffffu, status, 0);
+            if (status != 0) break;
+        }
+        if (lane == 0) {
+            // integration.f90:579-601
+            if (status == 2) goto L115;
+            if (abserr == huge_()) goto L115;
+            if (ifail + ierro == 0) goto L110;
+            if (ierro == 3) abserr = abserr + correc;
+            if (ifail == 0) ifail = 3;
+            if (result != 0.0 && area != 0.0) goto L105;
+            if (abserr > errsum) goto L115;
+            if (area == 0.0) goto L130;
+            goto L110;
+L105:
+            if (abserr / fabs(result) > errsum / fabs(area)) goto L115;
+L110:
+            if (ksgn == (-1) && fmax2(fabs(result), fabs(area)) <= defabs * 1.0e-02) goto L130;
+            if (1.0e-02 > (result / area) || (result / area) > 1.0e+02 || errsum > fabs(area)) ifail = 6;
+            goto L130;
+L115:
+            result = 0.0;
+            for (k = 1; k <= last; k++) result = result + rlist[k];
+            abserr = errsum;
+L130:
+            if (ifail > 2) ifail = ifail - 1;
+        }
+    }
+    if (lane == 0) {
+        o.result = result;
+        o.abserr = abserr;
+        o.last = last;
+        o.ifail = ifail;
+    }
+    __syncwarp();
+}
+
+// instance -> (ixi, i, c, sub).  Results: cst_res[((ixi*n + i)*7 + c)*3 + sub], same index for last/ifail.
+// Warps pull instances from a global counter (costs vary by three orders of magnitude).
+constexpr int K2_WARPS = 4;
+
+__global__ void __launch_bounds__(K2_WARPS * 32)
+assemble_cst_kernel(int n, int nxi, const double* __restrict__ xi_arr, int grid_type,
+                    QagsScratch* __restrict__ scratch, unsigned long long* __restrict__ counter,
+                    double* __restrict__ cst_res, int* __restrict__ cst_last, int* __restrict__ cst_ifail)
+{
+    __shared__ double s_fv[K2_WARPS][42];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    QagsScratch* S = scratch + (size_t)blockIdx.x * K2_WARPS + warp;
+    double* fv = s_fv[warp];
+    const unsigned long long total = (unsigned long long)nxi * n * 21ULL;
+    for (;;) {
+        unsigned long long inst = 0;
+        if (lane == 0) inst = atomicAdd(counter, 1ULL);
+        inst = __shfl_sync(0xffffffffu, inst, 0);
+        if (inst >= total) break;
+        // order instances so that the expensive constants of one (xi,i) are spread over warps
+        const int sub = (int)(inst % 3ULL);
+        const int c = (int)((inst / 3ULL) % 7ULL);
+        const unsigned long long row = inst / 21ULL;
+        const int i = (int)(row % (unsigned long long)n) + 1;
+        const int ixi = (int)(row / (unsigned long long)n);
+        const double xi = xi_arr[ixi];
+        const double x = grid_node(i, n, xi, grid_type);
+        // adaptive_integrate's three sub-intervals (integration.f90:56-63)
+        const double eps = 1e-15;
+        const double ymin = -1.0 + eps, ymax = 1.0 - eps;
+        double a, b;
+        if (sub == 0) { a = ymin; b = -fabs(x) - eps; }
+        else if (sub == 1) { a = -fabs(x) + eps; b = fabs(x) - eps; }
+        else { a = fabs(x) + eps; b = ymax; }
+        QagsOut o;
+        switch (c) {
+        case 0: qags_warp<K_NSP>(x, xi, a, b, S, fv, lane, o); break;
+        case 1: qags_warp<K_NSM>(x, xi, a, b, S, fv, lane, o); break;
+        case 2: qags_warp<K_NSN>(x, xi, a, b, S, fv, lane, o); break;
+        case 3: qags_warp<K_V1GG>(x, xi, a, b, S, fv, lane, o); break;
+        case 4: qags_warp<K_A1GG>(x, xi, a, b, S, fv, lane, o); break;
+        case 5: qags_warp<K_V1GGN>(x, xi, a, b, S, fv, lane, o); break;
+        default: qags_warp<K_A1GGN>(x, xi, a, b, S, fv, lane, o); break;
+        }
+        if (lane == 0) {
+            const size_t idx = (size_t)inst;
+            cst_res[idx] = o.result;
+            cst_last[idx] = o.last;
+            cst_ifail[idx] = o.ifail;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// K3: composition of the nfl slice (matevo.f90:293, 331-335, 370-376, 389-396, 437-446, 463-472).
+// Output matrices are row-major per xi: NS (n x n): NS0, NS1p, NS1m; SG (2n x 2n): V0, A0, V1, A1.
+
+__global__ void compose_kernel(int n, int nxi, int nfl, const double* __restrict__ P, const double* __restrict__ diag,
+                               const double* __restrict__ cst_res,
+                               double* __restrict__ NS0, double* __restrict__ NS1p, double* __restrict__ NS1m,
+                               double* __restrict__ SGV0, double* __restrict__ SGA0,
+                               double* __restrict__ SGV1, double* __restrict__ SGA1)
+{
+    const size_t nn = (size_t)n * n;
+    const size_t total = nn * nxi;
+    const size_t fstride = total;
+    const double fn = (double)nfl;
+    const size_t m = (size_t)2 * n;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const size_t ixi = e / nn;
+        const size_t rem = e - ixi * nn;
+        const size_t i = rem / n, j = rem - i * n;
+        // pixel_conv = ((0 + reg) + pls) + cst; cst = Kcst(x,xi) * f_i(x_i) on the diagonal only
+        double c_k0qq = 0.0, c_nsp = 0.0, c_nsm = 0.0, c_nsn = 0.0, c_a0gg = 0.0, c_a0ggn = 0.0,
+               c_vgg = 0.0, c_agg = 0.0, c_vggn = 0.0, c_aggn = 0.0;
+        if (i == j) {
+            const double* d = diag + (ixi * n + i) * DIAG_N;
+            const double fx = d[DIAG_FX];
+            const double* q = cst_res + (ixi * n + i) * 21;
+            double integ[7];
+#pragma unroll
+            for (int c = 0; c < 7; c++) {
+                double s = 0.0;
+                s = s + q[c * 3 + 0];
+                s = s + q[c * 3 + 1];
+                s = s + q[c * 3 + 2];
+                integ[c] = s;
+            }
+            c_k0qq = d[DIAG_K0QQ] * fx;
+            c_a0gg = d[DIAG_A0GG] * fx;
+            c_a0ggn = d[DIAG_A0GGN] * fx;
+            c_nsp = (nlo_explicit_cst(0) + integ[0]) * fx;
+            c_nsm = integ[1] * fx;
+            c_nsn = integ[2] * fx;
+            c_vgg = integ[3] * fx;
+            c_agg = integ[4] * fx;                                  // explicit term overwritten in the reference
+            c_vggn = (nlo_explicit_cst(5) + integ[5]) * fx;
+            c_aggn = (nlo_explicit_cst(6) + integ[6]) * fx;
+        }
+#define PV(k) P[(size_t)(k) * fstride + e]
+        const double ns0 = PV(K_K0QQ) + c_k0qq;
+        const double nsn = PV(K_NSN) + c_nsn;
+        const double ns1p = (PV(K_NSP) + c_nsp) + nsn * fn;
+        const double ns1m = (PV(K_NSM) + c_nsm) + nsn * fn;
+        NS0[e] = ns0;
+        NS1p[e] = ns1p;
+        NS1m[e] = ns1m;
+        const size_t base = ixi * m * m;
+        const size_t qq = base + i * m + j, qg = base + i * m + (j + n);
+        const size_t gq = base + (i + n) * m + j, gg = base + (i + n) * m + (j + n);
+        const double a_qg = fn * PV(K_A0QG);
+        const double a_gq = PV(K_A0GQ);
+        const double a_gg = (PV(K_A0GG) + c_a0gg) + fn * (0.0 + c_a0ggn);
+        SGA0[qq] = ns0; SGA0[qg] = a_qg; SGA0[gq] = a_gq; SGA0[gg] = a_gg;
+        SGV0[qq] = 0.0 + ns0;
+        SGV0[qg] = fn * PV(K_VMA0QG) + a_qg;
+        SGV0[gq] = PV(K_VMA0GQ) + a_gq;
+        SGV0[gg] = PV(K_VMA0GG) + a_gg;
+        SGV1[qq] = fn * PV(K_V1QQ) + ns1p;
+        SGV1[qg] = fn * PV(K_V1QG);
+        SGV1[gq] = PV(K_V1GQ) + fn * PV(K_V1GQN);
+        SGV1[gg] = (PV(K_V1GG) + c_vgg) + fn * (PV(K_V1GGN) + c_vggn);
+        SGA1[qq] = fn * PV(K_A1QQ) + ns1m;
+        SGA1[qg] = fn * PV(K_A1QG);
+        SGA1[gq] = PV(K_A1GQ) + fn * PV(K_A1GQN);
+        SGA1[gg] = (PV(K_A1GG) + c_agg) + fn * (PV(K_A1GGN) + c_aggn);
+#undef PV
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// test hooks: single kernel / dilog / log / pow evaluations (used by the parity tests through the C-ABI)
+
+__global__ void eval_kernels_kernel(int npts, const double* __restrict__ xs, const double* __restrict__ ys,
+                                    const double* __restrict__ xis, double* __restrict__ out /*[npts][NKERN]*/)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npts) return;
+    const double x = xs[p], y = ys[p], xi = xis[p];
+    const double X1 = 0.5 * (1.0 + x / xi), X2 = 0.5 * (1.0 - x / xi);
+    const double Y1 = 0.5 * (1.0 + y / xi), Y2 = 0.5 * (1.0 - y / xi);
+    double h1[NKERN], h2[NKERN];
+    eval_half<MASK_ALL>(X1, Y1, X2, Y2, h1);
+    eval_half<MASK_ALL>(X2, Y2, X1, Y1, h2);
+    for (int f = 0; f < NKERN; f++) out[(size_t)p * NKERN + f] = combine_halves_rt(f, h1[f], h2[f], xi);
+}
+
+__global__ void eval_scalar_kernel(int which, int npts, const double* __restrict__ a, const double* __restrict__ b,
+                                   double* __restrict__ out)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npts) return;
+    switch (which) {
+    case 0: out[p] = log_(a[p]); break;
+    case 1: out[p] = pow_(a[p], b[p]); break;
+    case 2: out[p] = dilog(a[p]); break;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// host launchers
+
+#define TKB_LAUNCH_CHECK()                                                   \
+    do {                                                                     \
+        cudaError_t e_ = cudaGetLastError();                                 \
+        ++g_launches;                                                        \
+        if (e_ != cudaSuccess) return set_error(cudaGetErrorString(e_));     \
+    } while (0)
+
+int launch_assemble_fixed(int n, int nxi, const double* xi_dev, int grid_type, double* P, double* diag, cudaStream_t st)
+{
+    dim3 grid(n, nxi);
+    assemble_fixed_kernel<<<grid, K1_THREADS, 0, st>>>(n, nxi, xi_dev, grid_type, P, diag);
+    TKB_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_assemble_cst(int n, int nxi, const double* xi_dev, int grid_type, void* scratch, int nblocks,
+                        unsigned long long* counter, double* cst_res, int* cst_last, int* cst_ifail, cudaStream_t st)
+{
+    cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st);
+    if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
+    assemble_cst_kernel<<<nblocks, K2_WARPS * 32, 0, st>>>(n, nxi, xi_dev, grid_type, (QagsScratch*)scratch, counter,
+                                                           cst_res, cst_last, cst_ifail);
+    TKB_LAUNCH_CHECK();
+    return 0;
+}
+int assemble_cst_warps_per_block() { return K2_WARPS; }
+
+int launch_compose(int n, int nxi, int nfl, const double* P, const double* diag, const double* cst_res,
+                   double* NS0, double* NS1p, double* NS1m, double* SGV0, double* SGA0, double* SGV1, double* SGA1,
+                   cudaStream_t st)
+{
+    const size_t total = (size_t)n * n * nxi;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    compose_kernel<<<blocks, 256, 0, st>>>(n, nxi, nfl, P, diag, cst_res, NS0, NS1p, NS1m, SGV0, SGA0, SGV1, SGA1);
+    TKB_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_eval_kernels(int npts, const double* xs, const double* ys, const double* xis, double* out, cudaStream_t st)
+{
+    eval_kernels_kernel<<<(npts + 63) / 64, 64, 0, st>>>(npts, xs, ys, xis, out);
+    TKB_LAUNCH_CHECK();
+    return 0;
+}
+int launch_eval_scalar(int which, int npts, const double* a, const double* b, double* out, cudaStream_t st)
+{
+    eval_scalar_kernel<<<(npts + 127) / 128, 128, 0, st>>>(which, npts, a, b, out);
+    TKB_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace tkb

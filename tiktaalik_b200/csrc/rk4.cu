@@ -1,0 +1,230 @@
+// rk4.cu -- Q^2 stepping of the evolution matrices on sm_100a: batched FP64 GEMM chain.
+//
+// Reference path replaced (file:line): matevo.f90:485-595 (make_evomat_NS/V_SG/A_SG) and
+// :600-673 (rk4_NS / rk4_SG): per xi and per Q^2 interval
+//     P_. = a_. K0 (+ a_.^2 K1),  W1 = P_i,  W2 = P_m + h/2 P_m W1,  W3 = P_m + h/2 P_m W2,
+//     W4 = P_e + h P_e W3,  M_new = (I + h/6 (W1 + 2 W2 + 2 W3 + W4)) M_old
+// with gfortran's matmul intrinsic.  Here every xi is one batch entry of a strided-batched
+// GEMM whose epilogue fuses the "D + alpha * (A B)" update, so one interval is 4 GEMM
+// launches + 2 elementwise launches per matrix type, all xi at once.
+// Matrices are row-major; tcgen05 has no FP64 kind, so this is a register-tiled DFMA kernel
+// (shared-memory staged tiles, 16x16 threads, TxT micro-tile per thread).
+#include <cuda_runtime.h>
+#include "tkb_internal.h"
+
+namespace tkb {
+
+#define TKB_LAUNCH_CHECK()                                                   \
+    do {                                                                     \
+        cudaError_t e_ = cudaGetLastError();                                 \
+        ++g_launches;                                                        \
+        if (e_ != cudaSuccess) return set_error(cudaGetErrorString(e_));     \
+    } while (0)
+
+constexpr int GEMM_BK = 16;
+
+// C = D + alpha * A B.  Block tile (16 T) x (16 T); thread (ty, tx) owns rows ty + 16 a, cols tx + 16 b.
+template <int T>
+__global__ void __launch_bounds__(256)
+gemm_kernel(int M, int N, int K, double alpha,
+            const double* __restrict__ A, int lda, int64_t strideA,
+            const double* __restrict__ B, int ldb, int64_t strideB, int bdivB,
+            const double* __restrict__ D, int ldd, int64_t strideD,
+            double* __restrict__ C, int ldc, int64_t strideC)
+{
+    constexpr int BM = 16 * T, BN = 16 * T;
+    __shared__ double As[GEMM_BK][BM + 1];      // As[k][m] (transposed on load)
+    __shared__ double Bs[GEMM_BK][BN];          // Bs[k][n]
+    const int b = blockIdx.z;
+    A += (int64_t)b * strideA;
+    B += (int64_t)(b / bdivB) * strideB;
+    C += (int64_t)b * strideC;
+    if (D) D += (int64_t)b * strideD;
+    const int row0 = blockIdx.y * BM, col0 = blockIdx.x * BN;
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+
+    double acc[T][T];
+#pragma unroll
+    for (int a = 0; a < T; a++)
+#pragma unroll
+        for (int c = 0; c < T; c++) acc[a][c] = 0.0;
+
+    for (int k0 = 0; k0 < K; k0 += GEMM_BK) {
+        // A tile: BM rows x 16 cols, each row 128 contiguous bytes
+        for (int e = tid; e < BM * GEMM_BK; e += 256) {
+            const int r = e >> 4, kk = e & 15;
+            const int gr = row0 + r, gk = k0 + kk;
+            As[kk][r] = (gr < M && gk < K) ? A[(int64_t)gr * lda + gk] : 0.0;
+        }
+        // B tile: 16 rows x BN cols
+        for (int e = tid; e < GEMM_BK * BN; e += 256) {
+            const int kk = e / BN, c = e - kk * BN;
+            const int gk = k0 + kk, gc = col0 + c;
+            Bs[kk][c] = (gk < K && gc < N) ? B[(int64_t)gk * ldb + gc] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < GEMM_BK; kk++) {
+            double av[T], bv[T];
+#pragma unroll
+            for (int a = 0; a < T; a++) av[a] = As[kk][ty + 16 * a];
+#pragma unroll
+            for (int c = 0; c < T; c++) bv[c] = Bs[kk][tx + 16 * c];
+#pragma unroll
+            for (int a = 0; a < T; a++)
+#pragma unroll
+                for (int c = 0; c < T; c++) acc[a][c] = fma(av[a], bv[c], acc[a][c]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int a = 0; a < T; a++) {
+        const int gr = row0 + ty + 16 * a;
+        if (gr >= M) continue;
+#pragma unroll
+        for (int c = 0; c < T; c++) {
+            const int gc = col0 + tx + 16 * c;
+            if (gc >= N) continue;
+            double v = alpha * acc[a][c];
+            if (D) v = D[(int64_t)gr * ldd + gc] + v;
+            C[(int64_t)gr * ldc + gc] = v;
+        }
+    }
+}
+
+int launch_gemm(int M, int N, int K, double alpha,
+                const double* A, int lda, int64_t strideA,
+                const double* B, int ldb, int64_t strideB, int bdivB,
+                const double* D, int ldd, int64_t strideD,
+                double* C, int ldc, int64_t strideC, int batch, cudaStream_t st)
+{
+    if (batch <= 0 || M <= 0 || N <= 0) return 0;
+    if (bdivB < 1) bdivB = 1;
+    // 80-wide tiles divide nx = 80/160/320 exactly; otherwise 64-wide; narrow N uses 32-wide
+    const bool t5 = (M % 80 == 0) && (N % 80 == 0);
+    const int maxz = 65535;
+    for (int b0 = 0; b0 < batch; b0 += maxz) {
+        const int nb = (batch - b0 < maxz) ? (batch - b0) : maxz;
+        if ((b0 % bdivB) != 0) return set_error("launch_gemm: batch chunk not aligned with bdivB");
+        const double* Ab = A + (int64_t)b0 * strideA;
+        const double* Bb = B + (int64_t)(b0 / bdivB) * strideB;
+        const double* Db = D ? D + (int64_t)b0 * strideD : nullptr;
+        double* Cb = C + (int64_t)b0 * strideC;
+        if (t5) {
+            dim3 grid((N + 79) / 80, (M + 79) / 80, nb);
+            gemm_kernel<5><<<grid, 256, 0, st>>>(M, N, K, alpha, Ab, lda, strideA, Bb, ldb, strideB, bdivB, Db, ldd,
+                                                 strideD, Cb, ldc, strideC);
+        } else if (N <= 32) {
+            dim3 grid((N + 31) / 32, (M + 31) / 32, nb);
+            gemm_kernel<2><<<grid, 256, 0, st>>>(M, N, K, alpha, Ab, lda, strideA, Bb, ldb, strideB, bdivB, Db, ldd,
+                                                 strideD, Cb, ldc, strideC);
+        } else {
+            dim3 grid((N + 63) / 64, (M + 63) / 64, nb);
+            gemm_kernel<4><<<grid, 256, 0, st>>>(M, N, K, alpha, Ab, lda, strideA, Bb, ldb, strideB, bdivB, Db, ldd,
+                                                 strideD, Cb, ldc, strideC);
+        }
+        TKB_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+// P_. = a_. K0 (+ a_.^2 K1)   (matevo.f90:617-626)
+__global__ void build_P_kernel(size_t count, double a_i, double a_m, double a_e, int nlo,
+                               const double* __restrict__ K0, const double* __restrict__ K1,
+                               double* __restrict__ Pi, double* __restrict__ Pm, double* __restrict__ Pe)
+{
+    const double ai2 = a_i * a_i, am2 = a_m * a_m, ae2 = a_e * a_e;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < count; e += (size_t)gridDim.x * blockDim.x) {
+        const double k0 = K0[e];
+        double pi = a_i * k0, pm = a_m * k0, pe = a_e * k0;
+        if (nlo) {
+            const double k1 = K1[e];
+            pi = pi + ai2 * k1;
+            pm = pm + am2 * k1;
+            pe = pe + ae2 * k1;
+        }
+        Pi[e] = pi; Pm[e] = pm; Pe[e] = pe;
+    }
+}
+
+// S = I + h/6 (W1 + 2 W2 + 2 W3 + W4)   (matevo.f90:633, 517-520)
+__global__ void rk4_combine_kernel(int m, size_t count, double h, const double* __restrict__ W1,
+                                   const double* __restrict__ W2, const double* __restrict__ W3,
+                                   const double* __restrict__ W4, double* __restrict__ S)
+{
+    const double h6 = h / 6.0;
+    const size_t mm = (size_t)m * m;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < count; e += (size_t)gridDim.x * blockDim.x) {
+        const size_t rem = e % mm;
+        const size_t i = rem / m, j = rem - i * m;
+        const double k = h6 * (W1[e] + 2.0 * W2[e] + 2.0 * W3[e] + W4[e]);
+        S[e] = ((i == j) ? 1.0 : 0.0) + k;
+    }
+}
+
+__global__ void set_identity_kernel(int m, int batch, double* __restrict__ M, int64_t stride)
+{
+    const size_t mm = (size_t)m * m;
+    const size_t count = mm * batch;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < count; e += (size_t)gridDim.x * blockDim.x) {
+        const size_t b = e / mm, rem = e - b * mm;
+        const size_t i = rem / m, j = rem - i * m;
+        M[(int64_t)b * stride + rem] = (i == j) ? 1.0 : 0.0;
+    }
+}
+
+// kernel getters (matevo.f90:124-241): out[ixi][i][j] = a K0[blk] (+ a^2 K1[blk]); K0/K1 are m x m per xi,
+// the n x n block starts at (roff, coff)
+__global__ void scale_add_kernel(size_t count, double a, double a2, int nlo, const double* __restrict__ K0,
+                                 const double* __restrict__ K1, int n, int m, int roff, int coff,
+                                 double* __restrict__ out)
+{
+    const size_t nn = (size_t)n * n;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < count; e += (size_t)gridDim.x * blockDim.x) {
+        const size_t ixi = e / nn, rem = e - ixi * nn;
+        const size_t i = rem / n, j = rem - i * n;
+        const size_t src = ixi * (size_t)m * m + (i + roff) * (size_t)m + (j + coff);
+        double v = a * K0[src];
+        if (nlo) v = v + a2 * K1[src];
+        out[e] = v;
+    }
+}
+
+static int ew_blocks(size_t count)
+{
+    size_t b = (count + 255) / 256;
+    if (b > 148 * 32) b = 148 * 32;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+int launch_build_P(size_t count, double a_i, double a_m, double a_e, int nlo, const double* K0, const double* K1,
+                   double* Pi, double* Pm, double* Pe, cudaStream_t st)
+{
+    build_P_kernel<<<ew_blocks(count), 256, 0, st>>>(count, a_i, a_m, a_e, nlo, K0, K1, Pi, Pm, Pe);
+    TKB_LAUNCH_CHECK();
+    return 0;
+}
+int launch_rk4_combine(int m, int batch, double h, const double* W1, const double* W2, const double* W3,
+                       const double* W4, double* S, cudaStream_t st)
+{
+    const size_t count = (size_t)m * m * batch;
+    rk4_combine_kernel<<<ew_blocks(count), 256, 0, st>>>(m, count, h, W1, W2, W3, W4, S);
+    TKB_LAUNCH_CHECK();
+    return 0;
+}
+int launch_set_identity(int m, int batch, double* M, int64_t stride, cudaStream_t st)
+{
+    set_identity_kernel<<<ew_blocks((size_t)m * m * batch), 256, 0, st>>>(m, batch, M, stride);
+    TKB_LAUNCH_CHECK();
+    return 0;
+}
+int launch_scale_add(size_t count, double a, double a2, int nlo, const double* K0, int64_t, const double* K1,
+                     int n, int m, int roff, int coff, double* out, cudaStream_t st)
+{
+    scale_add_kernel<<<ew_blocks(count), 256, 0, st>>>(count, a, a2, nlo, K0, K1, n, m, roff, coff, out);
+    TKB_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace tkb
