@@ -98,6 +98,9 @@ int tkb_eval_scalar(int which, int npts, const double* a_dev, const double* b_de
 /* device time in ms of the stages of the last tkb_make_kernels / tkb_make_matrices:
  * ms[0] fixed quadrature, ms[1] QAGS constants, ms[2] RK4 stepping (incl. composition) */
 int tkb_stage_ms(double ms[3]);
+/* measured DFMA throughput of the current device (8 independent FMA chains per thread, no memory
+ * traffic): the FP64 roofline denominator, which MEASURED_PEAKS.json does not carry */
+int tkb_fp64_peak(double* tflops);
 /* number of kernel launches issued by the library since load */
 long long tkb_launch_count(void);
 

@@ -416,4 +416,34 @@ int tkb_stage_ms(double ms[3])
 
 long long tkb_launch_count(void) { return g_launches; }
 
+int tkb_fp64_peak(double* tflops)
+{
+    int dev = 0, sms = 148;
+    CUDA_OK(cudaGetDevice(&dev));
+    CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    double* scratch = nullptr;
+    CUDA_OK(cudaMalloc(&scratch, 64));
+    cudaEvent_t e0, e1;
+    CUDA_OK(cudaEventCreate(&e0));
+    CUDA_OK(cudaEventCreate(&e1));
+    const int blocks = sms * 8, iters = 1 << 16;
+    double best = 0.0;
+    for (int rep = 0; rep < 6; rep++) {
+        CUDA_OK(cudaEventRecord(e0, 0));
+        if (launch_dfma_peak(blocks, iters, scratch, 0)) return 1;
+        CUDA_OK(cudaEventRecord(e1, 0));
+        CUDA_OK(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = 2.0 * 8.0 * (double)iters * 256.0 * (double)blocks;
+        const double tf = flops / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(scratch);
+    *tflops = best;
+    return 0;
+}
+
 }  // extern "C"

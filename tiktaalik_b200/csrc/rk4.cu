@@ -190,6 +190,26 @@ __global__ void scale_add_kernel(size_t count, double a, double a2, int nlo, con
     }
 }
 
+// FP64 roofline denominator: 8 independent DFMA chains per thread, no memory traffic
+__global__ void __launch_bounds__(256) dfma_peak_kernel(int iters, double seed, double* __restrict__ out)
+{
+    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 0.999999, c = 1e-9;
+    for (int i = 0; i < iters; i++) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    const double r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (r == 123.456) out[0] = r;
+}
+
+int launch_dfma_peak(int blocks, int iters, double* scratch, cudaStream_t st)
+{
+    dfma_peak_kernel<<<blocks, 256, 0, st>>>(iters, 1.0, scratch);
+    TKB_LAUNCH_CHECK();
+    return 0;
+}
+
 static int ew_blocks(size_t count)
 {
     size_t b = (count + 255) / 256;

@@ -40,6 +40,8 @@ int launch_set_identity(int m, int batch, double* M, int64_t stride, cudaStream_
 int launch_scale_add(size_t count, double a, double a2, int nlo, const double* K0, int64_t ld0, const double* K1,
                      int n, int m, int roff, int coff, double* out, cudaStream_t st);
 
+int launch_dfma_peak(int blocks, int iters, double* scratch, cudaStream_t st);
+
 // apply.cu
 int launch_apply(int m, int nxi, int nq2, int64_t S, const double* M, const double* g, int64_t ldg,
                  double* out, cudaStream_t st);
