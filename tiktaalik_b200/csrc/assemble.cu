@@ -224,20 +224,48 @@ assemble_fixed_kernel(int n, int nxi, const double* __restrict__ xi_arr, int gri
 }
 
 // ---------------------------------------------------------------------------------------
-// K2: QAGS (integration.f90:246-904), one instance per warp.
+// K2: QAGS (integration.f90:246-904), one instance per warp, one kernel launch per constant.
+//
+// Interval lists: the first QCAP entries of alist/blist/rlist/elist/iord live in shared
+// memory (typical instances need 25-60 intervals), entries beyond spill to a per-warp global
+// scratch (the reference's limit is 500, reached by the round-off dominated V-type gluon
+// constants at xi ~ 2e-5).
+// Evaluation: a bisection step needs the integrand at 2 x 21 nodes = 168 half-kernel tasks
+// (node, direction K(x,y) / K(y,x), half).  A half kernel whose support steps rho_step and
+// erbl_step both vanish is exactly zero (every piece is multiplied by one of them), so the
+// tasks are first classified, the live ones compacted with a warp ballot, and only those are
+// evaluated, 32 at a time.  A task is only skipped when every denominator and log argument of
+// any half kernel is non-zero (`safe`), so a 0*Inf = NaN of the reference is still reproduced.
 
 constexpr int QLIMIT = 500;
+constexpr int QCAP = 64;                 // indices 1..QCAP-1 in shared memory
 
-struct QagsScratch {            // per-warp interval lists, 1-based like the reference
+struct QagsScratch {                     // per-warp global spill (1-based indices >= QCAP)
     double alist[QLIMIT + 1], blist[QLIMIT + 1], rlist[QLIMIT + 1], elist[QLIMIT + 1];
-    double rlist2[53];
     int iord[QLIMIT + 1];
 };
-
 size_t qags_scratch_bytes() { return sizeof(QagsScratch); }
 
+struct QagsShared {                      // per-warp shared state
+    double alist[QCAP], blist[QCAP], rlist[QCAP], elist[QCAP];
+    double rlist2[53];
+    double fv[42];                       // integrand at the nodes of the current step
+    double hv[168];                      // half-kernel values of the current step
+    int iord[QCAP];
+    unsigned char live[168];             // compacted list of live task ids
+};
+
+template <typename T>
+struct SpillList {                       // 1-based list, head in shared memory, tail in global memory
+    T* s;
+    T* g;
+    __device__ __forceinline__ T& operator[](int i) const { return (i < QCAP) ? s[i] : g[i]; }
+};
+using DList = SpillList<double>;
+using IList = SpillList<int>;
+
 // integration.f90:616-729
-__device__ void qsort_(int limit, int last, int& maxerr, double& ermax, const double* elist, int* iord, int& nrmax)
+static __device__ __noinline__ void qsort_(int limit, int last, int& maxerr, double& ermax, DList elist, IList iord, int& nrmax)
 {
     int i, ibeg, isucc, j, jbnd, jupbn, k;
     double errmax, errmin;
@@ -288,7 +316,7 @@ L90:
 }
 
 // integration.f90:732-904
-__device__ void qextr_(int& n, double* epstab, double& result, double& abserr, double* res3la, int& nres)
+static __device__ __noinline__ void qextr_(int& n, double* epstab, double& result, double& abserr, double* res3la, int& nres)
 {
     int i, ib, ib2, ie, indx, k1, k2, k3, limexp, newelm, num;
     double delta1, delta2, delta3, epsinf, error, err1, err2, err3, e0, e1, e1abs, e2, e3, res, ss, tol1, tol2, tol3;
@@ -373,8 +401,8 @@ L100:
 
 // qk21's reductions from the 21 stored integrand values (integration.f90:159-222).
 // fv[q]: q = 0 centre, 2t-1 / 2t = value at centr -/+ hlgth*xgk(t).
-__device__ void qk21_reduce(const double* fv, double a, double b,
-                            double& result, double& abserr, double& resabs, double& resasc)
+static __device__ __noinline__ void qk21_reduce(const double* fv, double a, double b,
+                                                double& result, double& abserr, double& resabs, double& resasc)
 {
     const double hlgth = 5.0e-01 * (b - a);
     const double dhlgth = fabs(hlgth);
@@ -411,38 +439,82 @@ __device__ void qk21_reduce(const double* fv, double a, double b,
         abserr = fmax2((eps_() * 5.0e+01) * resabs, abserr);
 }
 
+// task -> the (X, Y, Xo, Yo) of its half kernel.  task = 4*node + 2*dir + half
+TKB_DEV void task_args(int task, double x, double xi, double a1, double b1, double a2, double b2,
+                       double& X, double& Y, double& Xo, double& Yo)
+{
+    const int node = task >> 2, dir = (task >> 1) & 1, half = task & 1;
+    const int iv = node / 21, q = node - 21 * iv;
+    const double a = iv ? a2 : a1, b = iv ? b2 : b1;
+    const double centr = 5.0e-01 * (a + b);
+    const double hlgth = 5.0e-01 * (b - a);
+    const double y = node_eta(centr, hlgth, q);
+    const double u = dir ? y : x, v = dir ? x : y;         // K(u, v, xi)
+    const double X1 = 0.5 * (1.0 + u / xi), X2 = 0.5 * (1.0 - u / xi);
+    const double Y1 = 0.5 * (1.0 + v / xi), Y2 = 0.5 * (1.0 - v / xi);
+    X = half ? X2 : X1; Y = half ? Y2 : Y1; Xo = half ? X1 : X2; Yo = half ? Y1 : Y2;
+}
+
+// true if the half kernel at (X, Y) may be skipped: both support steps vanish and no piece can be
+// non-finite (every denominator / log argument used by any half kernel is non-zero)
+TKB_DEV bool half_is_dead(double X, double Y, double Xo, double Yo)
+{
+    const double Xb = 1.0 - X, Yb = 1.0 - Y;
+    const double r = X / Y;
+    const double omr = 1.0 - r;
+    if (rho_step(r, omr, Y) != 0.0) return false;
+    if (theta_step(X) * theta_step(Xb) != 0.0) return false;
+    const double Xob = 1.0 - Xo, Xbb = 1.0 - Xb;
+    const bool finite = (fabs(X) <= huge_()) && (fabs(Y) <= huge_()) && (fabs(Xo) <= huge_()) && (fabs(Yo) <= huge_());
+    const bool nz = (X != 0.0) && (Y != 0.0) && (Xb != 0.0) && (Yb != 0.0) && (Xo != 0.0) && (Yo != 0.0) &&
+                    (Xob != 0.0) && (Xbb != 0.0) && (Y != X) && (Yo != Xo) && (Yb != Xb) && (Y != Xo) &&
+                    (Yb != Xob) && (Y != Xb) && (Yb != Xbb) && (omr != 0.0) && (r != 0.0) && (Y / X - 1.0 != 0.0) &&
+                    (1.0 - Xb / Y != 0.0) && (1.0 - Xo / Y != 0.0);
+    return finite && nz;
+}
+
 // Warp-cooperative evaluation of the integrand K(x,y,xi) - K(y,x,xi) (kernels_nlo.f90:71-77) at
-// the 21 nodes of `nint` intervals (1 or 2).  4 tasks per node: (direction, half).
+// the 21 nodes of `nint` intervals (1 or 2); result in sh.fv.
 template <int KID>
-__device__ __forceinline__ void eval_integrand_warp(double x, double xi, int nint,
-                                                    double a1, double b1, double a2, double b2,
-                                                    double* __restrict__ fv /* [42] shared */, int lane)
+__device__ __forceinline__ void eval_integrand_warp(double x, double xi, int nint, double a1, double b1,
+                                                    double a2, double b2, QagsShared& sh, int lane)
 {
     const int ntask = 84 * nint;
+    // classify and compact
+    int nlive = 0;
     for (int base = 0; base < ntask; base += 32) {
         const int task = base + lane;
-        const bool active = task < ntask;
-        double hval = 0.0;
-        const int node = task >> 2, dir = (task >> 1) & 1, half = task & 1;
-        if (active) {
-            const int iv = node / 21, q = node - 21 * iv;
-            const double a = iv ? a2 : a1, b = iv ? b2 : b1;
-            const double centr = 5.0e-01 * (a + b);
-            const double hlgth = 5.0e-01 * (b - a);
-            const double y = node_eta(centr, hlgth, q);
-            const double u = dir ? y : x, v = dir ? x : y;         // K(u, v, xi)
-            const double X1 = 0.5 * (1.0 + u / xi), X2 = 0.5 * (1.0 - u / xi);
-            const double Y1 = 0.5 * (1.0 + v / xi), Y2 = 0.5 * (1.0 - v / xi);
-            double out[NKERN];
-            if (half == 0) eval_half<bit(KID)>(X1, Y1, X2, Y2, out);
-            else eval_half<bit(KID)>(X2, Y2, X1, Y1, out);
-            hval = out[KID];
+        bool live = false;
+        if (task < ntask) {
+            double X, Y, Xo, Yo;
+            task_args(task, x, xi, a1, b1, a2, b2, X, Y, Xo, Yo);
+            live = !half_is_dead(X, Y, Xo, Yo);
+            if (!live) sh.hv[task] = 0.0;
         }
-        const double h2 = __shfl_xor_sync(0xffffffffu, hval, 1);
-        double K = 0.0;
-        if (active && half == 0) K = combine_halves<KID>(hval, h2, xi);
-        const double Kyx = __shfl_xor_sync(0xffffffffu, K, 2);
-        if (active && half == 0 && dir == 0) fv[node] = K - Kyx;
+        const unsigned m = __ballot_sync(0xffffffffu, live);
+        if (live) sh.live[nlive + __popc(m & ((1u << lane) - 1u))] = (unsigned char)task;
+        nlive += __popc(m);
+    }
+    __syncwarp();
+    // evaluate the live half kernels, 32 at a time
+    for (int base = 0; base < nlive; base += 32) {
+        const int idx = base + lane;
+        if (idx < nlive) {
+            const int task = sh.live[idx];
+            double X, Y, Xo, Yo;
+            task_args(task, x, xi, a1, b1, a2, b2, X, Y, Xo, Yo);
+            double out[NKERN];
+            eval_half<bit(KID)>(X, Y, Xo, Yo, out);
+            sh.hv[task] = out[KID];
+        }
+    }
+    __syncwarp();
+    // combine halves and directions
+    for (int node = lane; node < 21 * nint; node += 32) {
+        const double* h = sh.hv + 4 * node;
+        const double Kxy = combine_halves<KID>(h[0], h[1], xi);
+        const double Kyx = combine_halves<KID>(h[2], h[3], xi);
+        sh.fv[node] = Kxy - Kyx;
     }
     __syncwarp();
 }
@@ -451,26 +523,28 @@ struct QagsOut { double result, abserr; int last, ifail; };
 
 // One QAGS instance on one warp.  Lane 0 owns the scalar state.
 template <int KID>
-__device__ void qags_warp(double x, double xi, double a, double b, QagsScratch* __restrict__ S,
-                          double* __restrict__ fv, int lane, QagsOut& o)
+__device__ void qags_warp(double x, double xi, double a, double b, QagsShared& sh, QagsScratch* __restrict__ G,
+                          int lane, QagsOut& o)
 {
     const double epsabs = 1.0e-12, epsrel = 1.0e-06;       // iqags defaults (integration.f90:238-239)
     const int limit = QLIMIT;
     bool extrap = false, noext = false;
     int id, ierro = 0, iroff1 = 0, iroff2 = 0, iroff3 = 0, jupbnd, k, ksgn = 0, ktmin = 0, last = 0, maxerr = 1,
         nres = 0, nrmax = 1, numrl2 = 2, ifail = 0;
-    double abseps, area = 0, area1, area12, area2, a1 = 0, a2 = 0, b1 = 0, b2 = 0, correc = 0, defabs, defab1, defab2,
-           dres, erlarg = 0, erlast, errbnd, errmax = 0, error1, error2, erro12, errsum = 0, ertest = 0, resabs,
+    double abseps, area = 0, area1, area12, area2, a1 = 0, a2 = 0, b1 = 0, b2 = 0, correc = 0, defabs = 0, defab1, defab2,
+           dres, erlarg = 0, erlast = 0, errbnd, errmax = 0, error1, error2, erro12, errsum = 0, ertest = 0, resabs,
            reseps, res3la[4], small = 0, result = 0.0, abserr = 0.0;
-    double* alist = S->alist; double* blist = S->blist; double* rlist = S->rlist; double* elist = S->elist;
-    double* rlist2 = S->rlist2; int* iord = S->iord;
+    const DList alist{ sh.alist, G->alist }, blist{ sh.blist, G->blist }, rlist{ sh.rlist, G->rlist },
+        elist{ sh.elist, G->elist };
+    const IList iord{ sh.iord, G->iord };
+    double* rlist2 = sh.rlist2;
     int status = 0;     // lane 0: 0 continue loop, 1 exit loop (Fortran `exit`), 2 goto 115, 3 goto 140 (early return)
 
     // first approximation
-    eval_integrand_warp<KID>(x, xi, 1, a, b, a, b, fv, lane);
+    eval_integrand_warp<KID>(x, xi, 1, a, b, a, b, sh, lane);
     if (lane == 0) {
         alist[1] = a; blist[1] = b; rlist[1] = 0.0; elist[1] = 0.0;
-        qk21_reduce(fv, a, b, result, abserr, defabs, resabs);
+        qk21_reduce(sh.fv, a, b, result, abserr, defabs, resabs);
         dres = fabs(result);
         errbnd = fmax2(epsabs, epsrel * dres);
         last = 1;
@@ -491,7 +565,6 @@ __device__ void qags_warp(double x, double xi, double a, double b, QagsScratch* 
         }
     }
     status = __shfl_sync(0xffffffffu, status, 0);
-    __syncwarp();
 
     if (status != 3) {
         for (last = 2; last <= limit; last++) {
@@ -504,11 +577,11 @@ __device__ void qags_warp(double x, double xi, double a, double b, QagsScratch* 
             }
             a1 = __shfl_sync(0xffffffffu, a1, 0); b1 = __shfl_sync(0xffffffffu, b1, 0);
             a2 = __shfl_sync(0xffffffffu, a2, 0); b2 = __shfl_sync(0xffffffffu, b2, 0);
-            eval_integrand_warp<KID>(x, xi, 2, a1, b1, a2, b2, fv, lane);
+            eval_integrand_warp<KID>(x, xi, 2, a1, b1, a2, b2, sh, lane);
             if (lane == 0) {
                 status = 0;
-                qk21_reduce(fv, a1, b1, area1, error1, resabs, defab1);
-                qk21_reduce(fv + 21, a2, b2, area2, error2, resabs, defab2);
+                qk21_reduce(sh.fv, a1, b1, area1, error1, resabs, defab1);
+                qk21_reduce(sh.fv + 21, a2, b2, area2, error2, resabs, defab2);
                 area12 = area1 + area2;
                 erro12 = error1 + error2;
                 errsum = errsum + erro12 - errmax;
@@ -631,29 +704,29 @@ L130:
     __syncwarp();
 }
 
-// instance -> (ixi, i, c, sub).  Results: cst_res[((ixi*n + i)*7 + c)*3 + sub], same index for last/ifail.
-// Warps pull instances from a global counter (costs vary by three orders of magnitude).
+// One launch per constant c (kernel KID).  instance -> (ixi, i, sub); results go to
+// cst_res[((ixi*n + i)*7 + c)*3 + sub] (same index for last / ifail).  Warps pull instances from a
+// global counter: costs vary by three orders of magnitude between instances.
 constexpr int K2_WARPS = 4;
 
+template <int KID>
 __global__ void __launch_bounds__(K2_WARPS * 32)
-assemble_cst_kernel(int n, int nxi, const double* __restrict__ xi_arr, int grid_type,
+assemble_cst_kernel(int c, int n, int nxi, const double* __restrict__ xi_arr, int grid_type,
                     QagsScratch* __restrict__ scratch, unsigned long long* __restrict__ counter,
                     double* __restrict__ cst_res, int* __restrict__ cst_last, int* __restrict__ cst_ifail)
 {
-    __shared__ double s_fv[K2_WARPS][42];
+    __shared__ QagsShared s_state[K2_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    QagsScratch* S = scratch + (size_t)blockIdx.x * K2_WARPS + warp;
-    double* fv = s_fv[warp];
-    const unsigned long long total = (unsigned long long)nxi * n * 21ULL;
+    QagsScratch* G = scratch + (size_t)blockIdx.x * K2_WARPS + warp;
+    QagsShared& sh = s_state[warp];
+    const unsigned long long total = (unsigned long long)nxi * n * 3ULL;
     for (;;) {
         unsigned long long inst = 0;
         if (lane == 0) inst = atomicAdd(counter, 1ULL);
         inst = __shfl_sync(0xffffffffu, inst, 0);
         if (inst >= total) break;
-        // order instances so that the expensive constants of one (xi,i) are spread over warps
         const int sub = (int)(inst % 3ULL);
-        const int c = (int)((inst / 3ULL) % 7ULL);
-        const unsigned long long row = inst / 21ULL;
+        const unsigned long long row = inst / 3ULL;
         const int i = (int)(row % (unsigned long long)n) + 1;
         const int ixi = (int)(row / (unsigned long long)n);
         const double xi = xi_arr[ixi];
@@ -666,17 +739,9 @@ assemble_cst_kernel(int n, int nxi, const double* __restrict__ xi_arr, int grid_
         else if (sub == 1) { a = -fabs(x) + eps; b = fabs(x) - eps; }
         else { a = fabs(x) + eps; b = ymax; }
         QagsOut o;
-        switch (c) {
-        case 0: qags_warp<K_NSP>(x, xi, a, b, S, fv, lane, o); break;
-        case 1: qags_warp<K_NSM>(x, xi, a, b, S, fv, lane, o); break;
-        case 2: qags_warp<K_NSN>(x, xi, a, b, S, fv, lane, o); break;
-        case 3: qags_warp<K_V1GG>(x, xi, a, b, S, fv, lane, o); break;
-        case 4: qags_warp<K_A1GG>(x, xi, a, b, S, fv, lane, o); break;
-        case 5: qags_warp<K_V1GGN>(x, xi, a, b, S, fv, lane, o); break;
-        default: qags_warp<K_A1GGN>(x, xi, a, b, S, fv, lane, o); break;
-        }
+        qags_warp<KID>(x, xi, a, b, sh, G, lane, o);
         if (lane == 0) {
-            const size_t idx = (size_t)inst;
+            const size_t idx = ((size_t)row * 7 + (size_t)c) * 3 + (size_t)sub;
             cst_res[idx] = o.result;
             cst_last[idx] = o.last;
             cst_ifail[idx] = o.ifail;
@@ -809,13 +874,20 @@ int launch_assemble_fixed(int n, int nxi, const double* xi_dev, int grid_type, d
 }
 
 int launch_assemble_cst(int n, int nxi, const double* xi_dev, int grid_type, void* scratch, int nblocks,
-                        unsigned long long* counter, double* cst_res, int* cst_last, int* cst_ifail, cudaStream_t st)
+                        unsigned long long* counters /*[7]*/, double* cst_res, int* cst_last, int* cst_ifail, cudaStream_t st)
 {
-    cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st);
+    cudaError_t e = cudaMemsetAsync(counters, 0, 7 * sizeof(unsigned long long), st);
     if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
-    assemble_cst_kernel<<<nblocks, K2_WARPS * 32, 0, st>>>(n, nxi, xi_dev, grid_type, (QagsScratch*)scratch, counter,
-                                                           cst_res, cst_last, cst_ifail);
+    QagsScratch* S = (QagsScratch*)scratch;
+    const int T = K2_WARPS * 32;
+#define TKB_K2(c, KID)                                                                                          \
+    assemble_cst_kernel<KID><<<nblocks, T, 0, st>>>(c, n, nxi, xi_dev, grid_type, S, counters + c, cst_res,      \
+                                                    cst_last, cst_ifail);                                       \
     TKB_LAUNCH_CHECK();
+    // the expensive, long-tailed constants first
+    TKB_K2(3, K_V1GG) TKB_K2(4, K_A1GG) TKB_K2(0, K_NSP) TKB_K2(1, K_NSM)
+    TKB_K2(5, K_V1GGN) TKB_K2(6, K_A1GGN) TKB_K2(2, K_NSN)
+#undef TKB_K2
     return 0;
 }
 int assemble_cst_warps_per_block() { return K2_WARPS; }

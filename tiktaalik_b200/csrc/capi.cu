@@ -125,7 +125,7 @@ static int make_kernels_impl(int nx, int nxi, const double* xi_host, int grid_ty
     int dev = 0, sms = 148;
     CUDA_OK(cudaGetDevice(&dev));
     CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const unsigned long long total = (unsigned long long)rows * 21ULL;
+    const unsigned long long total = (unsigned long long)rows * 3ULL;       // instances per constant
     const int wpb = assemble_cst_warps_per_block();
     long long want = (long long)((total + wpb - 1) / wpb);
     int nblocks = sms * 4;
@@ -133,7 +133,7 @@ static int make_kernels_impl(int nx, int nxi, const double* xi_host, int grid_ty
     void* scratch = nullptr;
     unsigned long long* counter = nullptr;
     CUDA_OK(cudaMalloc(&scratch, qags_scratch_bytes() * (size_t)nblocks * wpb));
-    CUDA_OK(cudaMalloc(&counter, sizeof(unsigned long long)));
+    CUDA_OK(cudaMalloc(&counter, 8 * sizeof(unsigned long long)));
     int rc = launch_assemble_cst(nx, nxi, g.d_xi, grid_type, scratch, nblocks, counter, g.cst_res, g.cst_last,
                                  g.cst_ifail, st);
     CUDA_OK(cudaEventRecord(g.ev[2], st));
