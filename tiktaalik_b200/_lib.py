@@ -9,7 +9,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libtiktaalik_b200.so")
+SO_PATH = os.environ.get("TKB_LIB", os.path.join(_HERE, "libtiktaalik_b200.so"))   # TKB_LIB: tuning builds only
 _LIB = None
 
 _dp = C.POINTER(C.c_double)

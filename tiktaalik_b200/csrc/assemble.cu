@@ -710,7 +710,7 @@ L130:
 constexpr int K2_WARPS = 4;
 
 template <int KID>
-__global__ void __launch_bounds__(K2_WARPS * 32)
+__global__ void __launch_bounds__(K2_WARPS * 32, 4)
 assemble_cst_kernel(int c, int n, int nxi, const double* __restrict__ xi_arr, int grid_type,
                     QagsScratch* __restrict__ scratch, unsigned long long* __restrict__ counter,
                     double* __restrict__ cst_res, int* __restrict__ cst_last, int* __restrict__ cst_ifail)

@@ -128,7 +128,7 @@ static int make_kernels_impl(int nx, int nxi, const double* xi_host, int grid_ty
     const unsigned long long total = (unsigned long long)rows * 3ULL;       // instances per constant
     const int wpb = assemble_cst_warps_per_block();
     long long want = (long long)((total + wpb - 1) / wpb);
-    int nblocks = sms * 4;
+    int nblocks = sms * 8;        // more than fit at once: the spare blocks start as others drain
     if ((long long)nblocks > want) nblocks = (int)want;
     void* scratch = nullptr;
     unsigned long long* counter = nullptr;

@@ -85,42 +85,54 @@ TKB_DEV double dilog_at_half()
     return PI2 / 12.0 - (double)h;
 }
 
-// second-level call: argument produced by one reduction step
-TKB_DEV double dilog_inner(double w)
-{
-    if (w == 0.0) return 0.0;
-    if (w == 0.5) return dilog_at_half();
-    if (w == -1.0) return -PI2 / 12.0;     // unreachable from the reductions, kept for totality
-    if (w == 1.0) return PI2 / 6.0;
-    return dilog_half(w);
-}
-
+// Branch-uniform evaluation: every range of the reference's if-chain needs at most two logarithms
+// and one reduced dilogarithm, so the arguments are selected first and log_ / dilog_half are called
+// unconditionally -- lanes of a warp that fall into different ranges do not diverge.  Each range's
+// value is formed by exactly the reference's expression (specfun.f90:36-49).
 static __device__ __noinline__ double dilog(double z)
 {
+    // range id: 0 z<-1, 1 -1<z<0, 2 z>2, 3 1<z<2, 4 1/2<z<1, 5 rational core (0<z<1/2, NaN), 6 special value
+    int rg;
+    if (z == -1.0 || z == 0.0 || z == 0.5 || z == 1.0 || z == 2.0) rg = 6;
+    else if (z < -1.0) rg = 0;
+    else if (z < 0.0) rg = 1;
+    else if (z > 2.0) rg = 2;
+    else if (z > 1.0) rg = 3;
+    else if (z > 0.5) rg = 4;
+    else rg = 5;
+    const double omz = 1.0 - z;
+    // reduced argument w and the two log arguments
+    double w, la, lb;
+    switch (rg) {
+    case 0: w = 1.0 / omz; la = omz; lb = -z; break;
+    case 1: w = z / (z - 1.0); la = omz; lb = 1.0; break;
+    case 2: w = 1.0 / z; la = z; lb = 1.0; break;
+    case 3: w = 1.0 - 1.0 / z; la = z; lb = w; break;
+    case 4: w = omz; la = z; lb = omz; break;
+    default: w = z; la = 1.0; lb = 1.0; break;
+    }
+    const double l1 = log_(la);
+    const double l2 = log_(lb);
+    double D = dilog_half(w);
+    if (rg != 5 && rg != 6) {                 // the inner call of the reference sees the special points too
+        if (w == 0.0) D = 0.0;
+        else if (w == 0.5) D = dilog_at_half();
+        else if (w == 1.0) D = PI2 / 6.0;
+        else if (w == -1.0) D = -PI2 / 12.0;
+    }
+    switch (rg) {
+    case 0: return l1 * (0.5 * l1 - l2) - PI2 / 6.0 + D;
+    case 1: return -D - 0.5 * (l1 * l1);
+    case 2: return -D + PI2 / 3.0 - 0.5 * (l1 * l1);
+    case 3: return PI2 / 6.0 - l1 * (l2 + 0.5 * l1) + D;
+    case 4: return -D + PI2 / 6.0 - l1 * l2;
+    case 5: return D;
+    }
     if (z == -1.0) return -PI2 / 12.0;
     if (z == 0.0) return 0.0;
     if (z == 0.5) return dilog_at_half();
     if (z == 1.0) return PI2 / 6.0;
-    if (z == 2.0) return PI2 / 4.0;
-    if (z < -1.0) {
-        const double l = log_(1.0 - z);
-        return l * (0.5 * l - log_(-z)) - PI2 / 6.0 + dilog_inner(1.0 / (1.0 - z));
-    }
-    if (z < 0.0) {
-        const double l = log_(1.0 - z);
-        return -dilog_inner(z / (z - 1.0)) - 0.5 * (l * l);
-    }
-    if (z > 2.0) {
-        const double l = log_(z);
-        return -dilog_inner(1.0 / z) + PI2 / 3.0 - 0.5 * (l * l);
-    }
-    if (z > 1.0) {
-        const double l = log_(z);
-        const double w = 1.0 - 1.0 / z;
-        return PI2 / 6.0 - l * (log_(w) + 0.5 * l) + dilog_inner(w);
-    }
-    if (z > 0.5) return -dilog_inner(1.0 - z) + PI2 / 6.0 - log_(z) * log_(1.0 - z);
-    return dilog_half(z);
+    return PI2 / 4.0;
 }
 
 // ---------------------------------------------------------------------------------------
