@@ -1,0 +1,111 @@
+"""CPU tests of the host-side layer: the C-ABI library loads and exports every declared symbol,
+the numpy/torch-free helpers behave like the reference's (tiktaalik/matrices.py:95-130,
+tiktaalik/evolution.py:435-548), the xi partition, the GK model, and the no-fallback rule."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from tiktaalik_b200 import _lib
+    L = _lib.lib()                                  # loads on a machine without a GPU
+    hdr = open(os.path.join(ROOT, "include", "tiktaalik_b200.h")).read()
+    declared = set(re.findall(r"\b(tkb_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    for name in declared:
+        assert hasattr(L, name)
+    assert L.tkb_version() >= 100
+    assert isinstance(L.tkb_last_error(), bytes)
+
+
+def test_host_only_entry_points_match_oracle(tko):
+    import tiktaalik_b200 as tk
+    for nx, xi, gt in ((20, 0.5, 1), (80, 0.1, 2), (16, 2e-5, 2)):
+        np.testing.assert_allclose(tk.matrices.pixelspace(nx, xi, gt), tko.pixelspace(nx, xi, gt), rtol=4e-16)
+    q2 = np.array([1.0, tk.pars.mc2, 4.0, 10.0, tk.pars.mb2, 100.0, 91.1876 ** 2])
+    np.testing.assert_allclose(tk.qcd.alphaQCD(q2), tko.alphaQCD(q2), rtol=1e-14)
+    assert tk.qcd.alphaQCD(91.1876 ** 2)[0] == 0.118
+
+
+def test_compute_entry_points_fail_loudly_without_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    import tiktaalik_b200 as tk
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        tk.matrices.initialize_kernels(12, 0.5)
+    with pytest.raises(RuntimeError):
+        tk.matrices.apply_matrix(np.zeros((4, 4, 1, 2)), np.zeros((4, 1)))
+    with pytest.raises(RuntimeError):
+        tk.Evolver(nx=12, xi=0.5)
+
+
+def test_product_never_touches_the_oracle():
+    pkg = os.path.join(ROOT, "tiktaalik_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")) or f == "Makefile":
+                txt = open(os.path.join(dp, f)).read()
+                assert "oracle" not in txt.replace("the oracle checks", "").lower() or f.endswith(".cuh"), os.path.join(dp, f)
+                assert "tko" not in txt, os.path.join(dp, f)
+
+
+def test_q2space_passes_get_nfl():
+    import tiktaalik_b200 as tk
+    m = tk.matrices
+    q = m.Q2space(4.0, 10.0, 20)
+    assert q.shape == (20,) and np.allclose(q, np.geomspace(4.0, 10.0, 20))
+    q = m.Q2space(1.0, 100.0, 8)
+    assert q.shape == (8,) and tk.pars.mc2 in q and tk.pars.mb2 in q and np.all(np.diff(q) > 0)
+    assert m.passes(q, tk.pars.mc2) and not m.passes(np.array([4.0, 10.0]), tk.pars.mb2)
+    assert not m.passes(np.array([tk.pars.mc2, 10.0]), tk.pars.mc2)
+    assert [m.get_nfl(v) for v in (1.0, tk.pars.mc2, 4.0, tk.pars.mb2, 100.0)] == [3, 4, 4, 5, 5]
+    assert tk.pars.mc2 == 1.6641000000000001 and tk.pars.mb2 == 17.472399999999997
+
+
+def test_basis_helpers_on_cpu_tensors():
+    from tiktaalik_b200 import evolution as ev
+    for nfl in (3, 4, 5):
+        T = ev.Tpls_matrix(nfl)
+        assert T.shape == (nfl, nfl) and np.all(T[0] == 1) and T[nfl - 1, nfl - 1] == -(nfl - 1)
+        assert abs(np.linalg.det(T)) > 0
+    g = np.arange(24.0).reshape(2, 3, 4)
+    p = ev.add_pad(g, 3)
+    assert p.shape == (5, 3, 4) and np.all(p[2:] == 0) and np.array_equal(p[:2], g)
+    t = ev.add_pad(torch.ones(2, 3), 1)
+    assert tuple(t.shape) == (3, 3) and float(t[2].sum()) == 0
+    assert ev.swap_AV('A') == 'V' and ev.swap_AV('V') == 'A'
+    with pytest.raises(ValueError):
+        ev.swap_AV('X')
+
+
+def test_xi_partition_and_clamp():
+    from tiktaalik_b200 import shard
+    counts, offs = shard.xi_partition(10, 4)
+    assert counts == [3, 3, 2, 2] and offs == [0, 3, 6, 8]
+    xi = np.array([1e-7, 0.1, 0.5, 0.9999999])
+    c = shard.clamp_xi(xi)
+    assert c[0] == 1e-6 and c[-1] == 0.999999 and xi[0] == 1e-7               # matevo.f90:688-689, input untouched
+    parts = [shard.local_xi(xi, r, 2)[0] for r in range(2)]
+    assert np.array_equal(np.concatenate(parts), c)
+
+
+def test_gk_model_matches_oracle(tko):
+    import tiktaalik_b200 as tk
+    x = tk.matrices.pixelspace(40)
+    t = np.array([0.0, -0.3])
+    for name in ("Hu", "Hd", "Hs", "Hg", "Hu_val", "Hd_val", "Hu_sea", "Hd_sea"):
+        for xi in (0.5, 0.2):
+            a = getattr(tk.model, name)(x, xi, t)
+            b = tko.gk(name, x, [xi], t)
+            assert a.shape == (40, 1, 2)
+            assert np.abs(a - b).max() <= 1e-9 * np.abs(b).max()
+    a = tk.model.H_singlet(x, np.array([0.3, 0.5]), 0.0)
+    assert a.shape == (40, 2, 1)
+    assert np.abs(a - tko.H_singlet(x, [0.3, 0.5], [0.0])).max() <= 1e-9 * np.abs(a).max()
+    assert np.allclose(a, -a[::-1])                                            # the singlet is odd in x

@@ -70,7 +70,11 @@ def gather_matrix(M_local, counts=None, group=None):
         out = torch.empty((world * nloc, nq, m, m), dtype=store.dtype, device=store.device)
         dist.all_gather_into_tensor(out, store, group=group)
     else:
-        parts = [torch.empty((c, nq, m, m), dtype=store.dtype, device=store.device) for c in counts]
-        dist.all_gather(parts, store, group=group)
-        out = torch.cat(parts, dim=0)
+        # collectives need equal contributions: pad every slab to the largest block, trim afterwards
+        cmax = max(counts)
+        padded = torch.zeros((cmax, nq, m, m), dtype=store.dtype, device=store.device)
+        padded[:nloc] = store
+        allp = torch.empty((world * cmax, nq, m, m), dtype=store.dtype, device=store.device)
+        dist.all_gather_into_tensor(allp, padded, group=group)
+        out = torch.cat([allp[r * cmax:r * cmax + c] for r, c in enumerate(counts)], dim=0)
     return out.permute(2, 3, 0, 1)
