@@ -238,11 +238,9 @@ def main():
         nonlocal host, d2h_bytes
         tk.shard.f90src.make_kernels_shard(NX, xi, GRID_TYPE, 0, 0)
         tk.matrices.initialize_evolution_matrices(Q2, nlo=True)
-        mats = [getattr(tk.matrices, n)(**kw) for n, kw in names]
+        mats = [getattr(tk.matrices, n)(**kw).permute(2, 3, 0, 1) for n, kw in names]     # storage order, contiguous
         if host is None:
-            # pinned host buffers with the library's [xi][Q2][i][j] storage order: plain D2H memcpys
-            host = [torch.empty((m.shape[2], m.shape[3], m.shape[0], m.shape[1]), dtype=torch.float64)
-                    .pin_memory().permute(2, 3, 0, 1) for m in mats]
+            host = [torch.empty(tuple(m.shape), dtype=torch.float64).pin_memory() for m in mats]
             d2h_bytes = sum(m.numel() * 8 for m in mats)
         for h, m in zip(host, mats):
             h.copy_(m, non_blocking=True)

@@ -23,13 +23,13 @@ __global__ void __launch_bounds__(GEMV_WARPS * 32)
 apply_small_kernel(int m, int nq2, const double* __restrict__ M, const double* __restrict__ g, int64_t ldg,
                    double* __restrict__ out)
 {
-    extern __shared__ double s_g[];                 // [m][S]
+    extern __shared__ double s_g[];                 // [S][m]: sample-major so that lanes read consecutive words
     const int b = blockIdx.x;                       // b = k * nq2 + q
     const int k = b / nq2;
     const double* gk = g + (int64_t)k * S;
     for (int e = threadIdx.x; e < m * S; e += blockDim.x) {
         const int j = e / S, s = e - j * S;
-        s_g[e] = gk[(int64_t)j * ldg + s];
+        s_g[s * m + j] = gk[(int64_t)j * ldg + s];
     }
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -43,11 +43,12 @@ apply_small_kernel(int m, int nq2, const double* __restrict__ M, const double* _
         for (int s = 0; s < S; s++) acc[s] = 0.0;
         for (int j2 = lane; j2 < m / 2; j2 += 32) {
             const double2 v = row[j2];
-            const double* g0 = s_g + (2 * j2) * S;
 #pragma unroll
-            for (int s = 0; s < S; s++) acc[s] = fma(v.x, g0[s], acc[s]);
-#pragma unroll
-            for (int s = 0; s < S; s++) acc[s] = fma(v.y, g0[S + s], acc[s]);
+            for (int s = 0; s < S; s++) {
+                const double2 gv = reinterpret_cast<const double2*>(s_g + s * m)[j2];
+                acc[s] = fma(v.x, gv.x, acc[s]);
+                acc[s] = fma(v.y, gv.y, acc[s]);
+            }
         }
 #pragma unroll
         for (int s = 0; s < S; s++) {

@@ -251,9 +251,21 @@ struct QagsShared {                      // per-warp shared state
     double rlist2[53];
     double fv[42];                       // integrand at the nodes of the current step
     double hv[168];                      // half-kernel values of the current step
+    double ny[42][2];                    // per node: 0.5 (1 + y/xi), 0.5 (1 - y/xi)
     int iord[QCAP];
     unsigned char live[168];             // compacted list of live task ids
 };
+
+#ifdef TKB_K2_STATS
+__device__ unsigned long long g_k2stats[16];
+#define K2_T0() long long t0_ = clock64()
+#define K2_ACC(slot) do { if (lane == 0) atomicAdd(&g_k2stats[slot], (unsigned long long)(clock64() - t0_)); t0_ = clock64(); } while (0)
+#define K2_CNT(slot, v) do { if (lane == 0) atomicAdd(&g_k2stats[slot], (unsigned long long)(v)); } while (0)
+#else
+#define K2_T0()
+#define K2_ACC(slot)
+#define K2_CNT(slot, v)
+#endif
 
 template <typename T>
 struct SpillList {                       // 1-based list, head in shared memory, tail in global memory
@@ -439,76 +451,116 @@ static __device__ __noinline__ void qk21_reduce(const double* fv, double a, doub
         abserr = fmax2((eps_() * 5.0e+01) * resabs, abserr);
 }
 
-// task -> the (X, Y, Xo, Yo) of its half kernel.  task = 4*node + 2*dir + half
-TKB_DEV void task_args(int task, double x, double xi, double a1, double b1, double a2, double b2,
+// Per-node arguments of a step: sh.ny[node] = (0.5 (1 + y/xi), 0.5 (1 - y/xi)) for the 21 nodes of each
+// of the `nint` intervals (kernels_nlo.f90:52-55 applied to the integration variable).
+TKB_DEV void fill_nodes(QagsShared& sh, double xi, int nint, double a1, double b1, double a2, double b2, int lane)
+{
+    for (int node = lane; node < 21 * nint; node += 32) {
+        const int iv = node / 21, q = node - 21 * iv;
+        const double a = iv ? a2 : a1, b = iv ? b2 : b1;
+        const double centr = 5.0e-01 * (a + b);
+        const double hlgth = 5.0e-01 * (b - a);
+        const double y = node_eta(centr, hlgth, q);
+        const double t = y / xi;
+        sh.ny[node][0] = 0.5 * (1.0 + t);
+        sh.ny[node][1] = 0.5 * (1.0 - t);
+    }
+    __syncwarp();
+}
+
+// task -> the (X, Y, Xo, Yo) of its half kernel.  task = 4*node + 2*dir + half; dir 0 is K(x, y, xi),
+// dir 1 is K(y, x, xi).  (xx1, xx2) = (0.5 (1 + x/xi), 0.5 (1 - x/xi)) of the fixed point x.
+TKB_DEV void task_args(int task, const QagsShared& sh, double xx1, double xx2,
                        double& X, double& Y, double& Xo, double& Yo)
 {
     const int node = task >> 2, dir = (task >> 1) & 1, half = task & 1;
-    const int iv = node / 21, q = node - 21 * iv;
-    const double a = iv ? a2 : a1, b = iv ? b2 : b1;
-    const double centr = 5.0e-01 * (a + b);
-    const double hlgth = 5.0e-01 * (b - a);
-    const double y = node_eta(centr, hlgth, q);
-    const double u = dir ? y : x, v = dir ? x : y;         // K(u, v, xi)
-    const double X1 = 0.5 * (1.0 + u / xi), X2 = 0.5 * (1.0 - u / xi);
-    const double Y1 = 0.5 * (1.0 + v / xi), Y2 = 0.5 * (1.0 - v / xi);
-    X = half ? X2 : X1; Y = half ? Y2 : Y1; Xo = half ? X1 : X2; Yo = half ? Y1 : Y2;
+    const double yy1 = sh.ny[node][0], yy2 = sh.ny[node][1];
+    const double U1 = dir ? yy1 : xx1, U2 = dir ? yy2 : xx2;      // first argument's pair
+    const double V1 = dir ? xx1 : yy1, V2 = dir ? xx2 : yy2;      // second argument's pair
+    X = half ? U2 : U1; Y = half ? V2 : V1; Xo = half ? U1 : U2; Yo = half ? V1 : V2;
 }
 
-// true if the half kernel at (X, Y) may be skipped: both support steps vanish and no piece can be
-// non-finite (every denominator / log argument used by any half kernel is non-zero)
-TKB_DEV bool half_is_dead(double X, double Y, double Xo, double Yo)
+// Support class of the half kernel at (X, Y): 0 dead (both steps vanish), 1 erbl-only (rho_step == 0,
+// erbl_step != 0), 2 full.  Classes 0 and 1 are only reported when no skipped piece can be non-finite
+// (every denominator / log argument used by any half kernel is non-zero), otherwise 2.
+TKB_DEV int half_class(double X, double Y, double Xo, double Yo)
 {
     const double Xb = 1.0 - X, Yb = 1.0 - Y;
     const double r = X / Y;
     const double omr = 1.0 - r;
-    if (rho_step(r, omr, Y) != 0.0) return false;
-    if (theta_step(X) * theta_step(Xb) != 0.0) return false;
+    if (rho_step(r, omr, Y) != 0.0) return 2;
     const double Xob = 1.0 - Xo, Xbb = 1.0 - Xb;
     const bool finite = (fabs(X) <= huge_()) && (fabs(Y) <= huge_()) && (fabs(Xo) <= huge_()) && (fabs(Yo) <= huge_());
+    // log|Y/X - 1| must stay finite: |Y - X| > 4 eps |X| guarantees that the rounded quotient differs from 1
     const bool nz = (X != 0.0) && (Y != 0.0) && (Xb != 0.0) && (Yb != 0.0) && (Xo != 0.0) && (Yo != 0.0) &&
-                    (Xob != 0.0) && (Xbb != 0.0) && (Y != X) && (Yo != Xo) && (Yb != Xb) && (Y != Xo) &&
-                    (Yb != Xob) && (Y != Xb) && (Yb != Xbb) && (omr != 0.0) && (r != 0.0) && (Y / X - 1.0 != 0.0) &&
-                    (1.0 - Xb / Y != 0.0) && (1.0 - Xo / Y != 0.0);
-    return finite && nz;
+                    (Xob != 0.0) && (Xbb != 0.0) && (Yo != Xo) && (Yb != Xb) && (Y != Xo) &&
+                    (Yb != Xob) && (Y != Xb) && (Yb != Xbb) && (omr != 0.0) && (r != 0.0) &&
+                    (fabs(Y - X) > 4.0 * eps_() * fabs(X));
+    if (!(finite && nz)) return 2;
+    return (theta_step(X) * theta_step(Xb) != 0.0) ? 1 : 0;
 }
 
 // Warp-cooperative evaluation of the integrand K(x,y,xi) - K(y,x,xi) (kernels_nlo.f90:71-77) at
 // the 21 nodes of `nint` intervals (1 or 2); result in sh.fv.
 template <int KID>
-__device__ __forceinline__ void eval_integrand_warp(double x, double xi, int nint, double a1, double b1,
+__device__ __forceinline__ void eval_integrand_warp(double xx1, double xx2, double xi, int nint, double a1, double b1,
                                                     double a2, double b2, QagsShared& sh, int lane)
 {
+    K2_T0();
+    fill_nodes(sh, xi, nint, a1, b1, a2, b2, lane);
     const int ntask = 84 * nint;
-    // classify and compact
-    int nlive = 0;
+    constexpr bool HAS_ERBL = (KID != K_NSN);        // KV1_qq_half_nfl has no ERBL-only piece
+    // classify and compact: full tasks fill sh.live from the front, erbl-only tasks from the back
+    int nfull = 0, nerbl = 0;
     for (int base = 0; base < ntask; base += 32) {
         const int task = base + lane;
-        bool live = false;
+        int cls = 0;
         if (task < ntask) {
             double X, Y, Xo, Yo;
-            task_args(task, x, xi, a1, b1, a2, b2, X, Y, Xo, Yo);
-            live = !half_is_dead(X, Y, Xo, Yo);
-            if (!live) sh.hv[task] = 0.0;
+            task_args(task, sh, xx1, xx2, X, Y, Xo, Yo);
+            cls = half_class(X, Y, Xo, Yo);
+            if (!HAS_ERBL && cls == 1) cls = 0;
+            if (cls == 0) sh.hv[task] = 0.0;
         }
-        const unsigned m = __ballot_sync(0xffffffffu, live);
-        if (live) sh.live[nlive + __popc(m & ((1u << lane) - 1u))] = (unsigned char)task;
-        nlive += __popc(m);
+        const unsigned lt = (1u << lane) - 1u;
+        const unsigned mf = __ballot_sync(0xffffffffu, cls == 2);
+        const unsigned me = __ballot_sync(0xffffffffu, cls == 1);
+        if (cls == 2) sh.live[nfull + __popc(mf & lt)] = (unsigned char)task;
+        if (cls == 1) sh.live[167 - (nerbl + __popc(me & lt))] = (unsigned char)task;
+        nfull += __popc(mf);
+        nerbl += __popc(me);
     }
     __syncwarp();
+    K2_ACC(0); K2_CNT(8, nfull); K2_CNT(9, nerbl); K2_CNT(10, ntask); K2_CNT(11, (nfull + 31) / 32); K2_CNT(12, (nerbl + 31) / 32);
     // evaluate the live half kernels, 32 at a time
-    for (int base = 0; base < nlive; base += 32) {
+    for (int base = 0; base < nfull; base += 32) {
         const int idx = base + lane;
-        if (idx < nlive) {
+        if (idx < nfull) {
             const int task = sh.live[idx];
             double X, Y, Xo, Yo;
-            task_args(task, x, xi, a1, b1, a2, b2, X, Y, Xo, Yo);
+            task_args(task, sh, xx1, xx2, X, Y, Xo, Yo);
             double out[NKERN];
-            eval_half<bit(KID)>(X, Y, Xo, Yo, out);
+            eval_half<bit(KID), true>(X, Y, Xo, Yo, out);
             sh.hv[task] = out[KID];
         }
     }
     __syncwarp();
+    K2_ACC(1);
+    if (HAS_ERBL) {
+        for (int base = 0; base < nerbl; base += 32) {
+            const int idx = base + lane;
+            if (idx < nerbl) {
+                const int task = sh.live[167 - idx];
+                double X, Y, Xo, Yo;
+                task_args(task, sh, xx1, xx2, X, Y, Xo, Yo);
+                double out[NKERN];
+                eval_half<bit(KID), false>(X, Y, Xo, Yo, out);
+                sh.hv[task] = out[KID];
+            }
+        }
+    }
+    __syncwarp();
+    K2_ACC(2);
     // combine halves and directions
     for (int node = lane; node < 21 * nint; node += 32) {
         const double* h = sh.hv + 4 * node;
@@ -517,6 +569,7 @@ __device__ __forceinline__ void eval_integrand_warp(double x, double xi, int nin
         sh.fv[node] = Kxy - Kyx;
     }
     __syncwarp();
+    K2_ACC(3);
 }
 
 struct QagsOut { double result, abserr; int last, ifail; };
@@ -541,7 +594,8 @@ __device__ void qags_warp(double x, double xi, double a, double b, QagsShared& s
     int status = 0;     // lane 0: 0 continue loop, 1 exit loop (Fortran `exit`), 2 goto 115, 3 goto 140 (early return)
 
     // first approximation
-    eval_integrand_warp<KID>(x, xi, 1, a, b, a, b, sh, lane);
+    const double xx1 = 0.5 * (1.0 + x / xi), xx2 = 0.5 * (1.0 - x / xi);
+    eval_integrand_warp<KID>(xx1, xx2, xi, 1, a, b, a, b, sh, lane);
     if (lane == 0) {
         alist[1] = a; blist[1] = b; rlist[1] = 0.0; elist[1] = 0.0;
         qk21_reduce(sh.fv, a, b, result, abserr, defabs, resabs);
@@ -577,11 +631,20 @@ __device__ void qags_warp(double x, double xi, double a, double b, QagsShared& s
             }
             a1 = __shfl_sync(0xffffffffu, a1, 0); b1 = __shfl_sync(0xffffffffu, b1, 0);
             a2 = __shfl_sync(0xffffffffu, a2, 0); b2 = __shfl_sync(0xffffffffu, b2, 0);
-            eval_integrand_warp<KID>(x, xi, 2, a1, b1, a2, b2, sh, lane);
+            eval_integrand_warp<KID>(xx1, xx2, xi, 2, a1, b1, a2, b2, sh, lane);
+            K2_T0();
+            // the two qk21 reductions run side by side on lanes 0 and 1
+            {
+                double r_ = 0, e_ = 0, ra_ = 0, rc_ = 0;
+                if (lane < 2) qk21_reduce(sh.fv + 21 * lane, lane ? a2 : a1, lane ? b2 : b1, r_, e_, ra_, rc_);
+                area2 = __shfl_sync(0xffffffffu, r_, 1);
+                error2 = __shfl_sync(0xffffffffu, e_, 1);
+                defab2 = __shfl_sync(0xffffffffu, rc_, 1);
+                const double resabs2 = __shfl_sync(0xffffffffu, ra_, 1);
+                area1 = r_; error1 = e_; defab1 = rc_; resabs = resabs2;
+            }
             if (lane == 0) {
                 status = 0;
-                qk21_reduce(sh.fv, a1, b1, area1, error1, resabs, defab1);
-                qk21_reduce(sh.fv + 21, a2, b2, area2, error2, resabs, defab2);
                 area12 = area1 + area2;
                 erro12 = error1 + error2;
                 errsum = errsum + erro12 - errmax;
@@ -667,6 +730,7 @@ L80:
 Lend:
                 ;
             }
+            K2_ACC(4);
             status = __shfl_sync(0xffffffffu, status, 0);
             if (status != 0) break;
         }
@@ -888,6 +952,17 @@ int launch_assemble_cst(int n, int nxi, const double* xi_dev, int grid_type, voi
     TKB_K2(3, K_V1GG) TKB_K2(4, K_A1GG) TKB_K2(0, K_NSP) TKB_K2(1, K_NSM)
     TKB_K2(5, K_V1GGN) TKB_K2(6, K_A1GGN) TKB_K2(2, K_NSN)
 #undef TKB_K2
+#ifdef TKB_K2_STATS
+    {
+        cudaStreamSynchronize(st);
+        unsigned long long h[16];
+        cudaMemcpyFromSymbol(h, g_k2stats, sizeof h);
+        fprintf(stderr, "K2 stats (lane-0 cycles): classify %llu full-eval %llu erbl-eval %llu combine %llu bookkeeping %llu | tasks: full %llu erbl %llu total %llu | passes: full %llu erbl %llu\n",
+                h[0], h[1], h[2], h[3], h[4], h[8], h[9], h[10], h[11], h[12]);
+        unsigned long long z[16] = { 0 };
+        cudaMemcpyToSymbol(g_k2stats, z, sizeof z);
+    }
+#endif
     return 0;
 }
 int assemble_cst_warps_per_block() { return K2_WARPS; }

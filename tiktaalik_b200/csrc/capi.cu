@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <string>
 #include <vector>
 #include <cuda_runtime.h>
@@ -51,6 +52,11 @@ struct Context {
     int* cst_ifail = nullptr;
     Composed comp[3];           // nfl = 3, 4, 5
     double* M[4] = { nullptr, nullptr, nullptr, nullptr };   // NS+, NS-, SG V, SG A : [xi][Q2][i][j]
+    void* scratch = nullptr;    // QAGS spill lists + counters, kept across calls
+    size_t scratch_bytes = 0;
+    double* ws = nullptr;       // RK4 workspace, kept across calls
+    size_t ws_bytes = 0;
+    size_t M_elems = 0;         // elements of M[0] as allocated
     cudaEvent_t ev[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
     bool ev_k = false, ev_m = false;
 };
@@ -63,11 +69,16 @@ static void free_composed()
         c.valid = false;
     }
 }
+static void invalidate_matrices()
+{
+    g.nq2 = 0;
+    g.q2.clear();
+}
 static void free_matrices()
 {
     for (auto& p : g.M) { if (p) cudaFree(p); p = nullptr; }
-    g.nq2 = 0;
-    g.q2.clear();
+    g.M_elems = 0;
+    invalidate_matrices();
 }
 static void free_kernels()
 {
@@ -95,9 +106,12 @@ static int make_kernels_impl(int nx, int nxi, const double* xi_host, int grid_ty
 {
     if (nx < 6 || (nx % 2) != 0) return set_error("tkb_make_kernels: nx must be even and >= 6");
     if (nxi < 1 || !xi_host) return set_error("tkb_make_kernels: need at least one xi");
-    // matevo.f90:70: everything is deallocated first
-    free_matrices();
-    free_kernels();
+    // matevo.f90:70: everything is deallocated first.  Device buffers are kept when the sizes repeat
+    // (an xi sweep re-enters with the same nx, nxi): the contents are invalidated, not the allocations.
+    const bool same = (g.P != nullptr) && g.nx == nx && g.nxi == nxi;
+    invalidate_matrices();
+    if (!same) { free_matrices(); free_kernels(); }
+    for (auto& c : g.comp) c.valid = false;
     if (ensure_events()) return 1;
     g.nx = nx;
     g.nxi = nxi;
@@ -109,12 +123,14 @@ static int make_kernels_impl(int nx, int nxi, const double* xi_host, int grid_ty
 
     const size_t nn = (size_t)nx * nx * nxi;
     const size_t rows = (size_t)nx * nxi;
-    CUDA_OK(cudaMalloc(&g.d_xi, sizeof(double) * nxi));
-    CUDA_OK(cudaMalloc(&g.P, sizeof(double) * nn * NKERN_));
-    CUDA_OK(cudaMalloc(&g.diag, sizeof(double) * rows * DIAG_N));
-    CUDA_OK(cudaMalloc(&g.cst_res, sizeof(double) * rows * 21));
-    CUDA_OK(cudaMalloc(&g.cst_last, sizeof(int) * rows * 21));
-    CUDA_OK(cudaMalloc(&g.cst_ifail, sizeof(int) * rows * 21));
+    if (!same) {
+        CUDA_OK(cudaMalloc(&g.d_xi, sizeof(double) * nxi));
+        CUDA_OK(cudaMalloc(&g.P, sizeof(double) * nn * NKERN_));
+        CUDA_OK(cudaMalloc(&g.diag, sizeof(double) * rows * DIAG_N));
+        CUDA_OK(cudaMalloc(&g.cst_res, sizeof(double) * rows * 21));
+        CUDA_OK(cudaMalloc(&g.cst_last, sizeof(int) * rows * 21));
+        CUDA_OK(cudaMalloc(&g.cst_ifail, sizeof(int) * rows * 21));
+    }
     CUDA_OK(cudaMemcpyAsync(g.d_xi, g.xi.data(), sizeof(double) * nxi, cudaMemcpyHostToDevice, st));
 
     CUDA_OK(cudaEventRecord(g.ev[0], st));
@@ -129,19 +145,22 @@ static int make_kernels_impl(int nx, int nxi, const double* xi_host, int grid_ty
     const int wpb = assemble_cst_warps_per_block();
     long long want = (long long)((total + wpb - 1) / wpb);
     int nblocks = sms * 8;        // more than fit at once: the spare blocks start as others drain
+    if (const char* env = getenv("TKB_K2_BLOCKS_PER_SM")) { const int v = atoi(env); if (v > 0) nblocks = sms * v; }   // tuning knob
     if ((long long)nblocks > want) nblocks = (int)want;
-    void* scratch = nullptr;
-    unsigned long long* counter = nullptr;
-    CUDA_OK(cudaMalloc(&scratch, qags_scratch_bytes() * (size_t)nblocks * wpb));
-    CUDA_OK(cudaMalloc(&counter, 8 * sizeof(unsigned long long)));
-    int rc = launch_assemble_cst(nx, nxi, g.d_xi, grid_type, scratch, nblocks, counter, g.cst_res, g.cst_last,
-                                 g.cst_ifail, st);
+    const size_t need = qags_scratch_bytes() * (size_t)nblocks * wpb + 64;
+    if (g.scratch_bytes < need) {
+        if (g.scratch) cudaFree(g.scratch);
+        g.scratch = nullptr;
+        g.scratch_bytes = 0;
+        CUDA_OK(cudaMalloc(&g.scratch, need));
+        g.scratch_bytes = need;
+    }
+    unsigned long long* counter = (unsigned long long*)g.scratch;                 // 8 counters, then the spill lists
+    int rc = launch_assemble_cst(nx, nxi, g.d_xi, grid_type, (char*)g.scratch + 64, nblocks, counter, g.cst_res,
+                                 g.cst_last, g.cst_ifail, st);
     CUDA_OK(cudaEventRecord(g.ev[2], st));
     g.ev_k = true;
-    // the scratch lists are only needed while the kernel runs
     cudaError_t e = cudaStreamSynchronize(st);
-    cudaFree(scratch);
-    cudaFree(counter);
     if (rc) return 1;
     if (e != cudaSuccess) {
         char buf[256];
@@ -206,15 +225,25 @@ static int make_matrices_impl(int nq2, const double* q2_host, int nlo, cudaStrea
 {
     if (!g.P) return set_error("tkb_make_matrices: call tkb_make_kernels first");
     if (nq2 < 2 || !q2_host) return set_error("tkb_make_matrices: need at least two Q2 values");
-    free_matrices();
+    const int n = g.nx, nxi = g.nxi;
+    const size_t nn = (size_t)n * n * nxi * nq2;
+    if (g.M_elems != nn) {
+        free_matrices();
+        for (int t = 0; t < 4; t++) CUDA_OK(cudaMalloc(&g.M[t], sizeof(double) * nn * (t < 2 ? 1 : 4)));
+        g.M_elems = nn;
+    }
     g.q2.assign(q2_host, q2_host + nq2);
     g.nq2 = nq2;
     g.lnlo = nlo ? 1 : 0;
-    const int n = g.nx, nxi = g.nxi;
-    const size_t nn = (size_t)n * n * nxi * nq2;
-    for (int t = 0; t < 4; t++) CUDA_OK(cudaMalloc(&g.M[t], sizeof(double) * nn * (t < 2 ? 1 : 4)));
-    double* ws = nullptr;
-    CUDA_OK(cudaMalloc(&ws, sizeof(double) * (size_t)4 * n * n * nxi * 7));
+    const size_t ws_need = sizeof(double) * (size_t)4 * n * n * nxi * 7;
+    if (g.ws_bytes < ws_need) {
+        if (g.ws) cudaFree(g.ws);
+        g.ws = nullptr;
+        g.ws_bytes = 0;
+        CUDA_OK(cudaMalloc(&g.ws, ws_need));
+        g.ws_bytes = ws_need;
+    }
+    double* ws = g.ws;
     CUDA_OK(cudaEventRecord(g.ev[3], st));
     int rc = 0;
     // composed-array indices: 0 NS0, 1 NS1p, 2 NS1m, 3 SGV0, 4 SGA0, 5 SGV1, 6 SGA1
@@ -231,7 +260,6 @@ static int make_matrices_impl(int nq2, const double* q2_host, int nlo, cudaStrea
     cudaEventRecord(g.ev[4], st);
     g.ev_m = true;
     cudaError_t e = cudaStreamSynchronize(st);
-    cudaFree(ws);
     if (rc) return 1;
     if (e != cudaSuccess) {
         char buf[256];
@@ -282,7 +310,7 @@ int tkb_get_lnlo(void) { return g.lnlo; }
 
 int tkb_evomatrix(int type, int nstype, const double** dev_ptr, int64_t shape[4], int64_t strides[4])
 {
-    if (!g.M[0]) return set_error("evolution matrices are not initialised: call tkb_make_matrices first");
+    if (!g.M[0] || g.nq2 == 0) return set_error("evolution matrices are not initialised: call tkb_make_matrices first");
     int m;
     const double* p = matrix_ptr(type, nstype, m);
     if (!p) return set_error("tkb_evomatrix: bad type / nstype");
@@ -294,7 +322,7 @@ int tkb_evomatrix(int type, int nstype, const double** dev_ptr, int64_t shape[4]
 }
 int tkb_evomatrix_copy(int type, int nstype, double* dev_out, void* stream)
 {
-    if (!g.M[0]) return set_error("evolution matrices are not initialised: call tkb_make_matrices first");
+    if (!g.M[0] || g.nq2 == 0) return set_error("evolution matrices are not initialised: call tkb_make_matrices first");
     int m;
     const double* p = matrix_ptr(type, nstype, m);
     if (!p) return set_error("tkb_evomatrix_copy: bad type / nstype");
@@ -368,6 +396,10 @@ int tkb_free(void)
 {
     free_matrices();
     free_kernels();
+    if (g.scratch) cudaFree(g.scratch);
+    if (g.ws) cudaFree(g.ws);
+    g.scratch = nullptr; g.ws = nullptr;
+    g.scratch_bytes = g.ws_bytes = 0;
     return 0;
 }
 

@@ -24,6 +24,8 @@ namespace tkb {
 constexpr int GEMM_BK = 16;
 
 // C = D + alpha * A B.  Block tile (16 T) x (16 T); thread (ty, tx) owns rows ty + 16 a, cols tx + 16 b.
+// Two shared-memory stages: the global loads of tile k+1 are issued into registers before the
+// DFMA block of tile k and stored to the other stage afterwards (one barrier per k-tile).
 template <int T>
 __global__ void __launch_bounds__(256)
 gemm_kernel(int M, int N, int K, double alpha,
@@ -33,8 +35,9 @@ gemm_kernel(int M, int N, int K, double alpha,
             double* __restrict__ C, int ldc, int64_t strideC)
 {
     constexpr int BM = 16 * T, BN = 16 * T;
-    __shared__ double As[GEMM_BK][BM + 1];      // As[k][m] (transposed on load)
-    __shared__ double Bs[GEMM_BK][BN];          // Bs[k][n]
+    constexpr int NA = (BM * GEMM_BK) / 256, NB = (GEMM_BK * BN) / 256;     // loads per thread and tile (= T)
+    __shared__ double As[2][GEMM_BK][BM + 1];      // As[stage][k][m] (transposed on store)
+    __shared__ double Bs[2][GEMM_BK][BN];          // Bs[stage][k][n]
     const int b = blockIdx.z;
     A += (int64_t)b * strideA;
     B += (int64_t)(b / bdivB) * strideB;
@@ -49,33 +52,59 @@ gemm_kernel(int M, int N, int K, double alpha,
 #pragma unroll
         for (int c = 0; c < T; c++) acc[a][c] = 0.0;
 
-    for (int k0 = 0; k0 < K; k0 += GEMM_BK) {
-        // A tile: BM rows x 16 cols, each row 128 contiguous bytes
-        for (int e = tid; e < BM * GEMM_BK; e += 256) {
-            const int r = e >> 4, kk = e & 15;
+    double ra[NA], rb[NB];
+    auto load_tile = [&](int k0) {
+#pragma unroll
+        for (int u = 0; u < NA; u++) {
+            const int e = tid + 256 * u;
+            const int r = e >> 4, kk = e & 15;             // A tile: BM rows x 16 cols, rows of 128 contiguous bytes
             const int gr = row0 + r, gk = k0 + kk;
-            As[kk][r] = (gr < M && gk < K) ? A[(int64_t)gr * lda + gk] : 0.0;
+            ra[u] = (gr < M && gk < K) ? __ldg(A + (int64_t)gr * lda + gk) : 0.0;
         }
-        // B tile: 16 rows x BN cols
-        for (int e = tid; e < GEMM_BK * BN; e += 256) {
-            const int kk = e / BN, c = e - kk * BN;
+#pragma unroll
+        for (int u = 0; u < NB; u++) {
+            const int e = tid + 256 * u;
+            const int kk = e / BN, c = e - kk * BN;        // B tile: 16 rows x BN cols
             const int gk = k0 + kk, gc = col0 + c;
-            Bs[kk][c] = (gk < K && gc < N) ? B[(int64_t)gk * ldb + gc] : 0.0;
+            rb[u] = (gk < K && gc < N) ? __ldg(B + (int64_t)gk * ldb + gc) : 0.0;
         }
-        __syncthreads();
+    };
+    auto store_tile = [&](int st) {
+#pragma unroll
+        for (int u = 0; u < NA; u++) {
+            const int e = tid + 256 * u;
+            As[st][e & 15][e >> 4] = ra[u];
+        }
+#pragma unroll
+        for (int u = 0; u < NB; u++) {
+            const int e = tid + 256 * u;
+            const int kk = e / BN;
+            Bs[st][kk][e - kk * BN] = rb[u];
+        }
+    };
+
+    load_tile(0);
+    store_tile(0);
+    __syncthreads();
+    int st = 0;
+    for (int k0 = 0; k0 < K; k0 += GEMM_BK) {
+        const bool more = (k0 + GEMM_BK) < K;
+        if (more) load_tile(k0 + GEMM_BK);
 #pragma unroll
         for (int kk = 0; kk < GEMM_BK; kk++) {
             double av[T], bv[T];
 #pragma unroll
-            for (int a = 0; a < T; a++) av[a] = As[kk][ty + 16 * a];
+            for (int a = 0; a < T; a++) av[a] = As[st][kk][ty + 16 * a];
 #pragma unroll
-            for (int c = 0; c < T; c++) bv[c] = Bs[kk][tx + 16 * c];
+            for (int c = 0; c < T; c++) bv[c] = Bs[st][kk][tx + 16 * c];
 #pragma unroll
             for (int a = 0; a < T; a++)
 #pragma unroll
                 for (int c = 0; c < T; c++) acc[a][c] = fma(av[a], bv[c], acc[a][c]);
         }
+        if (more) store_tile(st ^ 1);
         __syncthreads();
+        st ^= 1;
     }
 #pragma unroll
     for (int a = 0; a < T; a++) {

@@ -246,9 +246,15 @@ __device__ inline double combine_halves_rt(int kid, double h1, double h2, double
 // only by the non-singlet qq half kernels which take it as their "Xbar, Ybar"
 // (kernels_nlo.f90:56, 113).  out[k] is written for every k in MASK.
 
-template <unsigned MASK>
+// WITH_RHO = false evaluates only the pieces that carry erbl_step (the caller has established that
+// rho_step(X,Y) == 0 and that every skipped piece is finite, so the skipped terms are exact zeros);
+// it is implemented for the kernels the QAGS constants need.
+constexpr unsigned MASK_QAGS = bit(K_NSP) | bit(K_NSM) | bit(K_NSN) | bit(K_V1GG) | bit(K_A1GG) | bit(K_V1GGN) | bit(K_A1GGN);
+
+template <unsigned MASK, bool WITH_RHO = true>
 __device__ __forceinline__ void eval_half(double X, double Y, double Xo, double Yo, double* __restrict__ out)
 {
+    static_assert(WITH_RHO || (MASK & ~MASK_QAGS) == 0, "erbl-only evaluation exists for the QAGS kernels only");
     constexpr bool LO_ANY = (MASK & 0x7fu) != 0;
     constexpr bool NS = (MASK & (bit(K_NSP) | bit(K_NSM))) != 0;
     constexpr bool V1QQ = (MASK & bit(K_V1QQ)) != 0, A1QQ = (MASK & bit(K_A1QQ)) != 0;
@@ -260,15 +266,15 @@ __device__ __forceinline__ void eval_half(double X, double Y, double Xo, double 
     constexpr bool NSN = (MASK & bit(K_NSN)) != 0;
     // which shared values are needed
     constexpr bool HV = V1QG || A1QG || V1GQ || A1GQ || V1GG || A1GG;          // own-Xbar h / hbar users
-    constexpr bool N_lr = NS || NSN || V1QQ || A1QQ || V1QG || A1QG || V1GQ || A1GQ || V1GG || A1GG || V1GGN || A1GGN;
-    constexpr bool N_lomr = NS || V1QG || A1QG || V1GQ || A1GQ || V1GQN || A1GQN || V1GG || A1GG;
-    constexpr bool N_lyx1 = V1QG || A1QG || V1GQ || A1GQ;
-    constexpr bool N_lX = NS || V1QQ || A1QQ || V1QG || A1QG || V1GQ || A1GQ || V1GQN || A1GQN || V1GG || A1GG || V1GGN || A1GGN;
-    constexpr bool N_lXb = NS || V1QQ || HV || V1GQN || V1GGN || A1GGN;
-    constexpr bool N_lY = NS || V1QQ || HV || V1GGN || A1GGN;
-    constexpr bool N_DX = NS || HV;
-    constexpr bool N_DYb = NS || V1QQ || HV;
-    constexpr bool N_DXb = V1QQ;
+    constexpr bool N_lr = WITH_RHO && (NS || NSN || V1QQ || A1QQ || V1QG || A1QG || V1GQ || A1GQ || V1GG || A1GG || V1GGN || A1GGN);
+    constexpr bool N_lomr = WITH_RHO && (NS || V1QG || A1QG || V1GQ || A1GQ || V1GQN || A1GQN || V1GG || A1GG);
+    constexpr bool N_lyx1 = WITH_RHO && (V1QG || A1QG || V1GQ || A1GQ);
+    constexpr bool N_lX = (WITH_RHO || NS || V1GG || A1GG || V1GGN || A1GGN) && (NS || V1QQ || A1QQ || V1QG || A1QG || V1GQ || A1GQ || V1GQN || A1GQN || V1GG || A1GG || V1GGN || A1GGN);
+    constexpr bool N_lXb = WITH_RHO ? (NS || V1QQ || HV || V1GQN || V1GGN || A1GGN) : (V1GG || A1GG);
+    constexpr bool N_lY = WITH_RHO && (NS || V1QQ || HV || V1GGN || A1GGN);
+    constexpr bool N_DX = WITH_RHO && (NS || HV);
+    constexpr bool N_DYb = WITH_RHO && (NS || V1QQ || HV);
+    constexpr bool N_DXb = WITH_RHO && V1QQ;
 
     const double Xb = 1.0 - X, Yb = 1.0 - Y;
     const double r = X / Y;
@@ -292,7 +298,7 @@ __device__ __forceinline__ void eval_half(double X, double Y, double Xo, double 
     const double DS = DX + DYb;                           // dilog(X) + dilog(Ybar)
     // hbar(Xbar, Y) with the half's own Xbar = 1 - X
     double G = 0, DXbb = 0, Xbb = 0;
-    if (HV) {
+    if (HV && WITH_RHO) {
         Xbb = 1.0 - Xb;
         G = 2.0 * dilog(1.0 - Xb / Y) + sqlog(lY, Y);
         DXbb = dilog(Xbb);
@@ -314,33 +320,38 @@ __device__ __forceinline__ void eval_half(double X, double Y, double Xo, double 
         const double QQf = qq_fab(X, Y);
         if (NSN) {
             const double beta0 = R4_3 * TF;
-            out[K_NSN] = (-0.5 * CF * beta0 * (R5_3 * QQf + X / Y + QQf * lr)) * rho;
+            out[K_NSN] = WITH_RHO ? (-0.5 * CF * beta0 * (R5_3 * QQf + X / Y + QQf * lr)) * rho : 0.0;
         }
         if (NS) {
-            const double QQfbar = qq_fab(Xo, Yo);
-            const double QQh = h_pp(QQf, qq_fab(Xb, Yb), LPXbY, DS);
-            // QQ_hbar(Xo, Y): its X is Xo, its Xbar is 1 - Xo
             const double lXo = abslog(Xo);
-            const double Xob = 1.0 - Xo;
-            const double Go = 2.0 * dilog(1.0 - Xo / Y) + sqlog(lY, Y);
-            const double QQhbar = hbar_pp(qq_fab(Xo, Y), qq_fab(Xob, Yb), Go, DYb, prodlog(lXo, Xo, lY, Y), dilog(Xob));
-            const double beta0 = -R11_3 * CA;
-            const double piece1 = (CF * CF) * ((R4_3 - 2.0 * ZETA2) * QQf + 3.0 * X / Y
-                - (1.5 * QQf - 0.5 * X / Yo) * lr
-                - (QQf - QQfbar) * prodlog(lr, r, lomr, omr)
-                + (QQf + 0.5 * X / Yo) * L2r);
-            const double piece2 = -0.5 * CF * beta0 * (R5_3 * QQf + X / Y + QQf * lr);
-            const double base3 = R4_3 * QQf + 2.0 * X / Y + QQh;
             const double piece4 = -0.5 * X / Yo * (lX + L2X - 2.0 * prodlog(lX, X, lXo, Xo)) * (CF * CF);
-            const double p12 = piece1 * rho + piece2 * rho;
             const double p4 = piece4 * erbl;
-            if (MASK & bit(K_NSP)) {
-                const double piece3 = -CF * (CF - 0.5 * CA) * (base3 - 1.0 * QQhbar);
-                out[K_NSP] = p12 + piece3 * rho + p4;
-            }
-            if (MASK & bit(K_NSM)) {
-                const double piece3 = -CF * (CF - 0.5 * CA) * (base3 - (-1.0) * QQhbar);
-                out[K_NSM] = p12 + piece3 * rho + p4;
+            if (!WITH_RHO) {
+                if (MASK & bit(K_NSP)) out[K_NSP] = p4;
+                if (MASK & bit(K_NSM)) out[K_NSM] = p4;
+            } else {
+                const double QQfbar = qq_fab(Xo, Yo);
+                const double QQh = h_pp(QQf, qq_fab(Xb, Yb), LPXbY, DS);
+                // QQ_hbar(Xo, Y): its X is Xo, its Xbar is 1 - Xo
+                const double Xob = 1.0 - Xo;
+                const double Go = 2.0 * dilog(1.0 - Xo / Y) + sqlog(lY, Y);
+                const double QQhbar = hbar_pp(qq_fab(Xo, Y), qq_fab(Xob, Yb), Go, DYb, prodlog(lXo, Xo, lY, Y), dilog(Xob));
+                const double beta0 = -R11_3 * CA;
+                const double piece1 = (CF * CF) * ((R4_3 - 2.0 * ZETA2) * QQf + 3.0 * X / Y
+                    - (1.5 * QQf - 0.5 * X / Yo) * lr
+                    - (QQf - QQfbar) * prodlog(lr, r, lomr, omr)
+                    + (QQf + 0.5 * X / Yo) * L2r);
+                const double piece2 = -0.5 * CF * beta0 * (R5_3 * QQf + X / Y + QQf * lr);
+                const double base3 = R4_3 * QQf + 2.0 * X / Y + QQh;
+                const double p12 = piece1 * rho + piece2 * rho;
+                if (MASK & bit(K_NSP)) {
+                    const double piece3 = -CF * (CF - 0.5 * CA) * (base3 - 1.0 * QQhbar);
+                    out[K_NSP] = p12 + piece3 * rho + p4;
+                }
+                if (MASK & bit(K_NSM)) {
+                    const double piece3 = -CF * (CF - 0.5 * CA) * (base3 - (-1.0) * QQhbar);
+                    out[K_NSM] = p12 + piece3 * rho + p4;
+                }
             }
         }
     }
@@ -492,7 +503,22 @@ __device__ __forceinline__ void eval_half(double X, double Y, double Xo, double 
     }
 
     // ---------------- GG (kernels_nlo.f90:709-982) ----------------
-    if (V1GG || V1GGN) {
+    if ((V1GG || V1GGN) && !WITH_RHO) {
+        if (V1GG) {
+            const double piece4 = (CA * CA) * (
+                -2.0 * (X * X) / (Yb * Yb) * L2X
+                + (Xb * ((X * X) + (Xb * Xb) - 2.0 * Xb * (1.0 + 2.0 * X) * Yb) + Yb) / (Yb * Yb) * prodlog(lX, X, lXb, Xb)
+                + ((3.0 * X * ((X * X) + (Xb * Xb)) * (Yb - Y) - 4.0 * (X * X) * Y) / (Y * Yb)
+                   - X * (2.0 - 3.0 * X - 8.0 * (Xb * Xb)) / (Yb * Yb)) * lX);
+            out[K_V1GG] = piece4 * erbl;
+        }
+        if (V1GGN) {
+            const double piece5 = CF * TF * (
+                -2.0 * X * (1.0 - 3.0 * X - 2.0 * X * Yb) / (Yb * Yb) * lX + (X * X) / (Yb * Yb) * L2X);
+            out[K_V1GGN] = piece5 * erbl;
+        }
+    }
+    if ((V1GG || V1GGN) && WITH_RHO) {
         const double GGfV = gg_fV(X, Y);
         const double GGfc = gg_fc(X, Y);
         // the beta0 bracket shared by KV1_GG_half (piece2) and KV1_GG_half_nfl (piece2)
@@ -530,7 +556,20 @@ __device__ __forceinline__ void eval_half(double X, double Y, double Xo, double 
             out[K_V1GGN] = 0.0 + piece2 * rho + piece3 * rho + 0.0 + piece5 * erbl;
         }
     }
-    if (A1GG || A1GGN) {
+    if ((A1GG || A1GGN) && !WITH_RHO) {
+        if (A1GG) {
+            const double LPX = prodlog(lX, X, lXb, Xb);
+            const double piece4 = (CA * CA) * (
+                (3.0 * (Xb - X) * X / (Y * Yb) - 6.0 * X * Xb / (Yb * Yb) + (X * X) / (Yb * Yb)) * lX
+                - 2.0 * (X * X) / (Yb * Yb) * (L2X + LPX) + (3.0 * X - Y) / (Yb * Yb) * LPX);
+            out[K_A1GG] = piece4 * erbl;
+        }
+        if (A1GGN) {
+            const double piece5 = CF * TF * (X / (Yb * Yb) * (2.0 * lX + X * L2X));
+            out[K_A1GGN] = piece5 * erbl;
+        }
+    }
+    if ((A1GG || A1GGN) && WITH_RHO) {
         const double GGfA = gg_fA(X, Y);
         const double br = -R5_3 * GGfA - R5_2 * (X * X) / (Y * Y) + X * (Yb + X * Y) / ((Y * Y) * Yb)
             + (X * X) / (Yb * Yb) * lY + (Xb * Xb) / (Y * Y) * lXb;
