@@ -267,17 +267,18 @@ __device__ unsigned long long g_k2stats[16];
 #define K2_CNT(slot, v)
 #endif
 
-template <typename T>
-struct SpillList {                       // 1-based list, head in shared memory, tail in global memory
+template <typename T, int CAP>
+struct SpillList {                       // 1-based list, head (indices < CAP) in shared memory, tail in global memory
     T* s;
     T* g;
-    __device__ __forceinline__ T& operator[](int i) const { return (i < QCAP) ? s[i] : g[i]; }
+    __device__ __forceinline__ T& operator[](int i) const { return (i < CAP) ? s[i] : g[i]; }
 };
-using DList = SpillList<double>;
-using IList = SpillList<int>;
+using DList = SpillList<double, QCAP>;
+using IList = SpillList<int, QCAP>;
 
 // integration.f90:616-729
-static __device__ __noinline__ void qsort_(int limit, int last, int& maxerr, double& ermax, DList elist, IList iord, int& nrmax)
+template <typename DL, typename IL>
+static __device__ __noinline__ void qsort_(int limit, int last, int& maxerr, double& ermax, DL elist, IL iord, int& nrmax)
 {
     int i, ibeg, isucc, j, jbnd, jupbn, k;
     double errmax, errmin;
@@ -768,6 +769,10 @@ L130:
     __syncwarp();
 }
 
+}  // namespace tkb
+#include "assemble_cst_batched.cuh"
+namespace tkb {
+
 // One launch per constant c (kernel KID).  instance -> (ixi, i, sub); results go to
 // cst_res[((ixi*n + i)*7 + c)*3 + sub] (same index for last / ifail).  Warps pull instances from a
 // global counter: costs vary by three orders of magnitude between instances.
@@ -966,6 +971,58 @@ int launch_assemble_cst(int n, int nxi, const double* xi_dev, int grid_type, voi
     return 0;
 }
 int assemble_cst_warps_per_block() { return K2_WARPS; }
+
+// batched form: one persistent block per SM, QB instances advanced in lock-step rounds
+int launch_assemble_cst_batched(int n, int nxi, const double* xi_dev, int grid_type, void* lists, int nblocks,
+                                unsigned long long* counters /*[7]*/, double* cst_res, int* cst_last, int* cst_ifail,
+                                cudaStream_t st, cudaStream_t* side /*[7] or null*/, cudaEvent_t fork, cudaEvent_t* join)
+{
+    cudaError_t e = cudaMemsetAsync(counters, 0, 7 * sizeof(unsigned long long), st);
+    if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
+    if (side) {
+        // every constant runs on its own stream so that a draining launch does not hold up the next one
+        e = cudaEventRecord(fork, st);
+        if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
+        for (int k = 0; k < 7; k++) {
+            e = cudaStreamWaitEvent(side[k], fork, 0);
+            if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
+        }
+    }
+    const size_t smem = sizeof(QBatchShared);
+#define TKB_K2B(c, KID)                                                                                              \
+    e = cudaFuncSetAttribute(assemble_cst_batched_kernel<KID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    if (e != cudaSuccess) return set_error(cudaGetErrorString(e));                                                   \
+    assemble_cst_batched_kernel<KID><<<nblocks, QT, smem, side ? side[c] : st>>>(                                     \
+        c, n, nxi, xi_dev, grid_type, (QLists*)lists + (size_t)(side ? c : 0) * nblocks * QB, counters + c, cst_res,  \
+        cst_last, cst_ifail);                                                                                        \
+    TKB_LAUNCH_CHECK();
+    TKB_K2B(3, K_V1GG) TKB_K2B(4, K_A1GG) TKB_K2B(0, K_NSP) TKB_K2B(1, K_NSM)
+    TKB_K2B(5, K_V1GGN) TKB_K2B(6, K_A1GGN) TKB_K2B(2, K_NSN)
+#undef TKB_K2B
+    if (side) {
+        for (int k = 0; k < 7; k++) {
+            e = cudaEventRecord(join[k], side[k]);
+            if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
+            e = cudaStreamWaitEvent(st, join[k], 0);
+            if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
+        }
+    }
+#ifdef TKB_K2_STATS
+    {
+        cudaStreamSynchronize(st);
+        unsigned long long h[16];
+        cudaMemcpyFromSymbol(h, g_k2stats, sizeof h);
+        fprintf(stderr, "K2 batched stats (thread-0 cycles summed over blocks): S %llu N %llu C %llu E %llu K %llu | rounds %llu active-slot-rounds %llu (fill %.2f)\n",
+                h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[5] ? (double)h[6] / ((double)QB * h[5]) : 0.0);
+        unsigned long long z[16] = { 0 };
+        cudaMemcpyToSymbol(g_k2stats, z, sizeof z);
+    }
+#endif
+    return 0;
+}
+size_t qags_batched_bytes_per_block() { return qags_lists_bytes(); }
+int qags_batched_instances_per_block() { return QB; }
+int qags_batched_blocks_per_sm() { return QBLOCKS_PER_SM; }
 
 int launch_compose(int n, int nxi, int nfl, const double* P, const double* diag, const double* cst_res,
                    double* NS0, double* NS1p, double* NS1m, double* SGV0, double* SGA0, double* SGV1, double* SGA1,

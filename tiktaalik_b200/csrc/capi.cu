@@ -59,6 +59,8 @@ struct Context {
     size_t M_elems = 0;         // elements of M[0] as allocated
     cudaEvent_t ev[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
     bool ev_k = false, ev_m = false;
+    cudaStream_t side[7] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+    cudaEvent_t fork = nullptr, join[7] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
 };
 static Context g;
 
@@ -98,6 +100,13 @@ static int ensure_events()
 {
     for (auto& e : g.ev)
         if (!e) CUDA_OK(cudaEventCreate(&e));
+    if (!g.fork) {
+        CUDA_OK(cudaEventCreateWithFlags(&g.fork, cudaEventDisableTiming));
+        for (int k = 0; k < 7; k++) {
+            CUDA_OK(cudaStreamCreateWithFlags(&g.side[k], cudaStreamNonBlocking));
+            CUDA_OK(cudaEventCreateWithFlags(&g.join[k], cudaEventDisableTiming));
+        }
+    }
     return 0;
 }
 
@@ -147,17 +156,40 @@ static int make_kernels_impl(int nx, int nxi, const double* xi_host, int grid_ty
     int nblocks = sms * 8;        // more than fit at once: the spare blocks start as others drain
     if (const char* env = getenv("TKB_K2_BLOCKS_PER_SM")) { const int v = atoi(env); if (v > 0) nblocks = sms * v; }   // tuning knob
     if ((long long)nblocks > want) nblocks = (int)want;
-    const size_t need = qags_scratch_bytes() * (size_t)nblocks * wpb + 64;
-    if (g.scratch_bytes < need) {
-        if (g.scratch) cudaFree(g.scratch);
-        g.scratch = nullptr;
-        g.scratch_bytes = 0;
-        CUDA_OK(cudaMalloc(&g.scratch, need));
-        g.scratch_bytes = need;
-    }
-    unsigned long long* counter = (unsigned long long*)g.scratch;                 // 8 counters, then the spill lists
-    int rc = launch_assemble_cst(nx, nxi, g.d_xi, grid_type, (char*)g.scratch + 64, nblocks, counter, g.cst_res,
+    // K2 form: batched (default) or one instance per warp (TKB_K2_MODE=warp, kept for comparison)
+    const char* mode = getenv("TKB_K2_MODE");
+    const bool batched = !(mode && mode[0] == 'w');
+    int rc = 0;
+    if (batched) {
+        const int qb = qags_batched_instances_per_block();
+        int nb = sms * qags_batched_blocks_per_sm();
+        const long long wantb = (long long)((total + qb - 1) / qb);
+        if ((long long)nb > wantb) nb = (int)wantb;
+        const bool multi = !(getenv("TKB_K2_ONE_STREAM"));
+        const size_t need = qags_batched_bytes_per_block() * (size_t)nb * (multi ? 7 : 1) + 64;
+        if (g.scratch_bytes < need) {
+            if (g.scratch) cudaFree(g.scratch);
+            g.scratch = nullptr;
+            g.scratch_bytes = 0;
+            CUDA_OK(cudaMalloc(&g.scratch, need));
+            g.scratch_bytes = need;
+        }
+        rc = launch_assemble_cst_batched(nx, nxi, g.d_xi, grid_type, (char*)g.scratch + 64, nb,
+                                         (unsigned long long*)g.scratch, g.cst_res, g.cst_last, g.cst_ifail, st,
+                                         multi ? g.side : nullptr, g.fork, g.join);
+    } else {
+        const size_t need = qags_scratch_bytes() * (size_t)nblocks * wpb + 64;
+        if (g.scratch_bytes < need) {
+            if (g.scratch) cudaFree(g.scratch);
+            g.scratch = nullptr;
+            g.scratch_bytes = 0;
+            CUDA_OK(cudaMalloc(&g.scratch, need));
+            g.scratch_bytes = need;
+        }
+        unsigned long long* counter = (unsigned long long*)g.scratch;             // 8 counters, then the spill lists
+        rc = launch_assemble_cst(nx, nxi, g.d_xi, grid_type, (char*)g.scratch + 64, nblocks, counter, g.cst_res,
                                  g.cst_last, g.cst_ifail, st);
+    }
     CUDA_OK(cudaEventRecord(g.ev[2], st));
     g.ev_k = true;
     cudaError_t e = cudaStreamSynchronize(st);

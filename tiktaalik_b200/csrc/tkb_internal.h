@@ -18,6 +18,12 @@ int assemble_cst_warps_per_block();
 int launch_assemble_fixed(int n, int nxi, const double* xi_dev, int grid_type, double* P, double* diag, cudaStream_t st);
 int launch_assemble_cst(int n, int nxi, const double* xi_dev, int grid_type, void* scratch, int nblocks,
                         unsigned long long* counter, double* cst_res, int* cst_last, int* cst_ifail, cudaStream_t st);
+int launch_assemble_cst_batched(int n, int nxi, const double* xi_dev, int grid_type, void* lists, int nblocks,
+                                unsigned long long* counters, double* cst_res, int* cst_last, int* cst_ifail,
+                                cudaStream_t st, cudaStream_t* side, cudaEvent_t fork, cudaEvent_t* join);
+size_t qags_batched_bytes_per_block();
+int qags_batched_instances_per_block();
+int qags_batched_blocks_per_sm();
 int launch_compose(int n, int nxi, int nfl, const double* P, const double* diag, const double* cst_res,
                    double* NS0, double* NS1p, double* NS1m, double* SGV0, double* SGA0, double* SGV1, double* SGA1,
                    cudaStream_t st);
