@@ -27,7 +27,10 @@ namespace tkb {
 #endif
 constexpr int QB = TKB_QB;           // instances per block
 constexpr int QT = TKB_QT;           // threads per block
-constexpr int QBLOCKS_PER_SM = 2;    // two blocks per SM run out of phase: one's bookkeeping overlaps the other's evaluation
+#ifndef TKB_QBPS
+#define TKB_QBPS 2
+#endif
+constexpr int QBLOCKS_PER_SM = TKB_QBPS;   // blocks per SM run out of phase: one block's bookkeeping overlaps the others' evaluation
 constexpr int QHEAD = 48;            // list entries (1-based index < QHEAD) kept in shared memory
 
 struct QSlot {                       // scalar QUADPACK state of one instance (integration.f90:374-381)

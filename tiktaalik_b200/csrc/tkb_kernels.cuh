@@ -53,6 +53,12 @@ constexpr double R1_54 = TKB_R32(1, 54);
 // dilogarithm (specfun.f90:24-79).  The reference recurses once into [0, 1/2]; the inner
 // call can only see 0, 1/2 (float32 log(2.) constant, specfun.f90:33) or the rational core.
 
+__constant__ double c_dlp[6] = { 0.9999999999999999502e+0, -2.6883926818565423430e+0, 2.6477222699473109692e+0,
+                                 -1.1538559607887416355e+0, 2.0886077795020607837e-1, -1.0859777134152463084e-2 };
+__constant__ double c_dlq[7] = { 1.0000000000000000000e+0, -2.9383926818565635485e+0, 3.2712093293018635389e+0,
+                                 -1.7076702173954289421e+0, 4.1596017228400603836e-1, -3.9801343754084482956e-2,
+                                 8.2743668974466659035e-4 };
+
 TKB_DEV double dilog_half(double x)
 {
     const double x2 = x * x;
@@ -60,20 +66,20 @@ TKB_DEV double dilog_half(double x)
     const double x4 = x2 * x2;
     const double x5 = x4 * x;
     const double x6 = x3 * x3;
-    double px = 0.9999999999999999502e+0;
-    px = px + x * -2.6883926818565423430e+0;
-    px = px + x2 * 2.6477222699473109692e+0;
-    px = px + x3 * -1.1538559607887416355e+0;
-    px = px + x4 * 2.0886077795020607837e-1;
-    px = px + x5 * -1.0859777134152463084e-2;
+    double px = c_dlp[0];
+    px = px + x * c_dlp[1];
+    px = px + x2 * c_dlp[2];
+    px = px + x3 * c_dlp[3];
+    px = px + x4 * c_dlp[4];
+    px = px + x5 * c_dlp[5];
     px = px + x6 * 0.0;
-    double qx = 1.0000000000000000000e+0;
-    qx = qx + x * -2.9383926818565635485e+0;
-    qx = qx + x2 * 3.2712093293018635389e+0;
-    qx = qx + x3 * -1.7076702173954289421e+0;
-    qx = qx + x4 * 4.1596017228400603836e-1;
-    qx = qx + x5 * -3.9801343754084482956e-2;
-    qx = qx + x6 * 8.2743668974466659035e-4;
+    double qx = c_dlq[0];
+    qx = qx + x * c_dlq[1];
+    qx = qx + x2 * c_dlq[2];
+    qx = qx + x3 * c_dlq[3];
+    qx = qx + x4 * c_dlq[4];
+    qx = qx + x5 * c_dlq[5];
+    qx = qx + x6 * c_dlq[6];
     return x * px / qx;
 }
 
