@@ -272,7 +272,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "xi pts/s", "h2d_bytes_per_step": int(xi.nbytes + Q2.nbytes),
                     "d2h_bytes_per_step": int(d2h_bytes)},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "fp64", "kernel": "assemble_cst_kernel (K2, QAGS constants)",
+            "roofline": {"bound": "fp64", "kernel": "assemble_cst_batched_kernel<KID> x 7 launches (K2, QAGS constants)",
                          "achieved": k2_tflops, "peak": peak.value, "unit": "TFLOP/s",
                          "frac": k2_tflops / peak.value if peak.value else None, "traffic": fpe.get("traffic_bytes"),
                          "peak_source": "DFMA microbenchmark measured in this run (tkb_fp64_peak); MEASURED_PEAKS.json "

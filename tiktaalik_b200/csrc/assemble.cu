@@ -67,7 +67,7 @@ TKB_DEV double node_eta(double centr, double hlgth, int q)
 constexpr int K1_THREADS = 256;
 constexpr int NNODE = 126;
 
-__global__ void __launch_bounds__(K1_THREADS)
+__global__ void __launch_bounds__(K1_THREADS, 2)
 assemble_fixed_kernel(int n, int nxi, const double* __restrict__ xi_arr, int grid_type,
                       double* __restrict__ P, double* __restrict__ diag)
 {
