@@ -1,0 +1,37 @@
+"""torchrun check (N GPUs of one node): xi-sharded assembly + stepping + NCCL all-gather equals the
+unsharded result computed on every rank.  Run:
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 tools/check_shard_nccl.py
+"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import torch.distributed as dist
+import tiktaalik_b200 as tk
+
+rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+nx, gt = 24, 2
+xi = np.geomspace(1e-7, 0.9999999, 2 * world + 1)          # uneven split, both ends clamped
+Q2 = tk.matrices.Q2space(4.0, 30.0, 4)
+# reference: the whole list on this GPU
+tk.matrices.initialize_kernels(nx, xi, grid_type=gt)
+tk.matrices.initialize_evolution_matrices(Q2, nlo=True)
+full = {n: getattr(tk.matrices, n)().clone() for n in ("matrix_VNS", "matrix_ANS", "matrix_VSG", "matrix_ASG")}
+# sharded
+mine = tk.shard.initialize_kernels_sharded(nx, xi, grid_type=gt, rank=rank, world_size=world)
+tk.matrices.initialize_evolution_matrices(Q2, nlo=True)
+ok = True
+for n, ref in full.items():
+    got = tk.shard.gather_matrix(getattr(tk.matrices, n)())
+    same = tuple(got.shape) == tuple(ref.shape) and torch.equal(got, ref)
+    ok = ok and same
+flag = torch.tensor([1 if ok else 0], device="cuda")
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print("shard+gather check over %d GPUs (%d xi, local %d): %s" % (world, xi.shape[0], mine.shape[0], "OK" if flag.item() == 1 else "MISMATCH"))
+dist.destroy_process_group()
+sys.exit(0 if flag.item() == 1 else 1)
