@@ -259,6 +259,45 @@ def main():
     e2e_value = total_xi * args.steps / float(t_e.item())
     f90.zero_copy = False
 
+    # ---- second half of the BASELINE metric: evolved GPDs/s (config C4: stored NLO matrices nx=160, 128 xi,
+    # 16 Q2 applied to S synthetic samples), rank-local, device-timed; HBM-bound at S=1, FP64-bound at S=1024 ----
+    application = None
+    try:
+        hbm = load_json(os.path.join(ROOT, "MEASURED_PEAKS.json"), {}).get("hbm_gbs")
+        hbm_src = "measured (MEASURED_PEAKS.json)" if hbm else "fallback (B200_PROFILING.md)"
+        hbm = hbm or 6650.0
+        xi4 = np.geomspace(1e-3, 0.9, 128)
+        tk.matrices.initialize_kernels(NX, xi4, grid_type=2)
+        tk.matrices.initialize_evolution_matrices(tk.matrices.Q2space(4.0, 10.0, 16), nlo=True)
+        f90.zero_copy = True
+        Msg = tk.matrices.matrix_VSG()
+        f90.zero_copy = False
+        gen = torch.Generator(device=dev).manual_seed(1234)
+        application = {"workload": "C4: V-type singlet NLO matrices nx=160 (m=320), 128 xi, 16 Q2, S samples"}
+        for S in (1, 1024):
+            g = torch.rand((2 * NX, 128, S), generator=gen, dtype=torch.float64, device=dev)
+            tk.matrices.apply_matrix(Msg, g)
+            ts = []
+            for _ in range(5):
+                flush.zero_()
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record()
+                tk.matrices.apply_matrix(Msg, g)
+                a1.record()
+                torch.cuda.synchronize()
+                ts.append(a0.elapsed_time(a1))
+            t = float(np.median(ts)) * 1e-3
+            m = 2 * NX
+            byt = 8.0 * (m * m * 128 * 16 + m * 128 * S + m * 128 * S * 16)
+            flop = 2.0 * m * m * 128 * 16 * S
+            application["S=%d" % S] = {"ms": t * 1e3, "evolved_gpds_per_s": S / t, "GBps": byt / t / 1e9,
+                                       "frac_of_hbm": byt / t / 1e9 / hbm, "TFLOPs": flop / t / 1e12,
+                                       "frac_of_fp64": flop / t / 1e12 / peak.value}
+        application["hbm_peak_GBps"] = hbm
+        application["hbm_peak_source"] = hbm_src
+    except Exception as exc:      # the headline line must still be printed
+        application = {"error": repr(exc)}
+
     if rank == 0:
         line = {
             "metric": "evolution-matrix sets/sec (xi pts/s) at nx=160 NLO", "value": value, "unit": "xi pts/s",
@@ -272,6 +311,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "xi pts/s", "h2d_bytes_per_step": int(xi.nbytes + Q2.nbytes),
                     "d2h_bytes_per_step": int(d2h_bytes)},
             "gpu_launches": int(launches),
+            "application": application,
             "roofline": {"bound": "fp64", "kernel": "assemble_cst_batched_kernel<KID> x 7 launches (K2, QAGS constants)",
                          "achieved": k2_tflops, "peak": peak.value, "unit": "TFLOP/s",
                          "frac": k2_tflops / peak.value if peak.value else None, "traffic": fpe.get("traffic_bytes"),
