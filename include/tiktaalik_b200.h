@@ -80,6 +80,12 @@ int tkb_alpha(int n, const double* q2_host, double* out_host);
 int tkb_apply(int m, int nxi, int nq2, int64_t S, const double* M_dev, const double* g_dev, int64_t ldg,
               double* out_dev, void* stream);
 
+/* replaces hu_wrap ... hd_sea_wrap (f90wrap/model.f90:16-158 -> model/gk.f90:75-241): the GK model GPD
+ * out[ix][ixi][it] = H_which(x[ix], xi[ixi], t[it]); which = 0 Hu, 1 Hd, 2 Hs, 3 Hg, 4 Hu_val, 5 Hd_val,
+ * 6 Hu_sea, 7 Hd_sea.  Input generator of the examples, not part of the timed path. */
+int tkb_gk(int which, int nx, int nxi, int nt, const double* x_dev, const double* xi_dev, const double* t_dev,
+           double* out_dev, void* stream);
+
 /* releases every device buffer of the implicit context */
 int tkb_free(void);
 

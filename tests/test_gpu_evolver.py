@@ -151,3 +151,19 @@ def test_evolver_api_contract(tk):
     assert tuple(tk.matrices.kernel_VGG().shape) == (12, 12, 1)
     with pytest.raises(AssertionError):
         tk.matrices.kernel_VQQ(nfl=6)
+
+
+def test_gk_model_on_device_bit_identical(tk, tko):
+    """tiktaalik.model API on the device (model/gk.f90:75-241) against the oracle's restatement"""
+    x = tko.pixelspace(40)
+    xi = np.array([0.05, 0.3, 0.7])
+    t = np.array([0.0, -0.25, -1.0])
+    for name in ("Hu", "Hd", "Hs", "Hg", "Hu_val", "Hd_val", "Hu_sea", "Hd_sea"):
+        got = getattr(tk.model, name)(x, xi, t)
+        assert got.is_cuda and tuple(got.shape) == (40, 3, 3)
+        ref = tko.gk(name, x, xi, t)
+        assert np.array_equal(got.cpu().numpy(), ref, equal_nan=True), name
+    s = tk.model.H_singlet(x, xi, t).cpu().numpy()
+    assert np.array_equal(s, tko.H_singlet(x, xi, t))
+    # scalars are accepted like in the reference (examples/examples.py:46)
+    assert tuple(tk.model.Hu(x, 0.5, t=0).shape) == (40, 1, 1)

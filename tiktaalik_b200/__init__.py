@@ -9,3 +9,4 @@ from . import matrices
 from . import model
 from . import pars
 from . import shard
+from . import cache

@@ -424,6 +424,13 @@ int tkb_apply(int m, int nxi, int nq2, int64_t S, const double* M_dev, const dou
     return launch_apply(m, nxi, nq2, S, M_dev, g_dev, ldg, out_dev, (cudaStream_t)stream);
 }
 
+int tkb_gk(int which, int nx, int nxi, int nt, const double* x_dev, const double* xi_dev, const double* t_dev,
+           double* out_dev, void* stream)
+{
+    if (which < 0 || which > 7 || nx < 0 || nxi < 0 || nt < 0) return set_error("tkb_gk: bad arguments");
+    return launch_gk(which, nx, nxi, nt, x_dev, xi_dev, t_dev, out_dev, (cudaStream_t)stream);
+}
+
 int tkb_free(void)
 {
     free_matrices();

@@ -52,6 +52,10 @@ int launch_dfma_peak(int blocks, int iters, double* scratch, cudaStream_t st);
 int launch_apply(int m, int nxi, int nq2, int64_t S, const double* M, const double* g, int64_t ldg,
                  double* out, cudaStream_t st);
 
+// gk.cu
+int launch_gk(int which, int nx, int nxi, int nt, const double* x, const double* xi, const double* t, double* out,
+              cudaStream_t st);
+
 // alpha.cpp (host): alpha_qcd.f90:22-127
 double alpha_qcd(double Q2);
 int neff(double Q2);

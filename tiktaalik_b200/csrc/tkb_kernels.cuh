@@ -53,9 +53,9 @@ constexpr double R1_54 = TKB_R32(1, 54);
 // dilogarithm (specfun.f90:24-79).  The reference recurses once into [0, 1/2]; the inner
 // call can only see 0, 1/2 (float32 log(2.) constant, specfun.f90:33) or the rational core.
 
-__constant__ double c_dlp[6] = { 0.9999999999999999502e+0, -2.6883926818565423430e+0, 2.6477222699473109692e+0,
+static __constant__ double c_dlp[6] = { 0.9999999999999999502e+0, -2.6883926818565423430e+0, 2.6477222699473109692e+0,
                                  -1.1538559607887416355e+0, 2.0886077795020607837e-1, -1.0859777134152463084e-2 };
-__constant__ double c_dlq[7] = { 1.0000000000000000000e+0, -2.9383926818565635485e+0, 3.2712093293018635389e+0,
+static __constant__ double c_dlq[7] = { 1.0000000000000000000e+0, -2.9383926818565635485e+0, 3.2712093293018635389e+0,
                                  -1.7076702173954289421e+0, 4.1596017228400603836e-1, -3.9801343754084482956e-2,
                                  8.2743668974466659035e-4 };
 
