@@ -20,10 +20,10 @@
 namespace tkb {
 
 #ifndef TKB_QB
-#define TKB_QB 20
+#define TKB_QB 16
 #endif
 #ifndef TKB_QT
-#define TKB_QT 256
+#define TKB_QT 384
 #endif
 constexpr int QB = TKB_QB;           // instances per block
 constexpr int QT = TKB_QT;           // threads per block
@@ -268,6 +268,45 @@ Lend:
     return QS_CONTINUE;
 }
 
+// every denominator / log argument that any half kernel of the node's four tasks can meet is non-zero
+// and finite, so a piece multiplied by a vanishing support step is an exact zero (not 0*Inf = NaN).
+// (a1, a2) = (0.5 (1 + x/xi), 0.5 (1 - x/xi)), (b1, b2) the same for y.
+TKB_DEV bool node_is_safe(double a1, double a2, double b1, double b2)
+{
+    const double big = huge_();
+    bool ok = (fabs(a1) <= big) && (fabs(a2) <= big) && (fabs(b1) <= big) && (fabs(b2) <= big);
+    const double v[4] = { a1, a2, b1, b2 };
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const double c = 1.0 - v[k];                 // Xbar / Ybar / 1 - Xo
+        ok = ok && (v[k] != 0.0) && (c != 0.0) && (1.0 - c != 0.0);
+    }
+    // pairs (X, Y) that appear as Y - X, Ybar - Xbar, Y - Xo, Ybar - (1 - Xo), Y - Xbar, Ybar - Xbb, Y/X - 1:
+    // any first-argument value against any second-argument value, in both directions
+    const double eps4 = 4.0 * eps_();
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int j = 2; j < 4; j++) {
+            const double p = v[i], q = v[j];
+            const double pb = 1.0 - p, qb = 1.0 - q;
+            ok = ok && (fabs(q - p) > eps4 * fabs(p)) && (fabs(p - q) > eps4 * fabs(q)) && (qb != pb) &&
+                 (q != pb) && (p != qb) && (qb != 1.0 - pb) && (pb != 1.0 - qb);
+        }
+    ok = ok && (a2 != a1) && (b2 != b1);             // Yo - Xo of the non-singlet halves: (a1,a2) vs (b1,b2) handled above
+    return ok;
+}
+
+// support class of the half kernel at (X, Y): 2 full, 1 erbl-only, 0 dead (see half_class)
+TKB_DEV int task_class(double X, double Y, bool safe)
+{
+    const double r = X / Y;
+    const double omr = 1.0 - r;
+    if (rho_step(r, omr, Y) != 0.0) return 2;
+    if (!safe || omr == 0.0 || r == 0.0) return 2;
+    return (theta_step(X) * theta_step(1.0 - X) != 0.0) ? 1 : 0;
+}
+
 template <int KID>
 __global__ void __launch_bounds__(QT, QBLOCKS_PER_SM)
 assemble_cst_batched_kernel(int c, int n, int nxi, const double* __restrict__ xi_arr, int grid_type,
@@ -363,56 +402,52 @@ assemble_cst_batched_kernel(int c, int n, int nxi, const double* __restrict__ xi
         const int any = __syncthreads_or(tid < QB && sh.slot[tid < QB ? tid : 0].nint != 0);
         if (!any) break;
         QB_ACC(0);
+        QB_ACC(1);
 #ifdef TKB_K2_STATS
         if (tid < QB && sh.slot[tid].nint != 0) atomicAdd(&g_k2stats[6], 1ULL);
         if (tid == 0) atomicAdd(&g_k2stats[5], 1ULL);
 #endif
 
-        // ---------------- N: node arguments ----------------
+        // ---------------- N + C: node arguments, support classes, compaction ----------------
+        // one thread per (instance, node): the four half-kernel tasks of a node are permutations of the
+        // same four numbers (xx1, xx2 of the fixed point, yy1, yy2 of the node), so the "no skipped piece
+        // can be non-finite" test is done once per node (conservatively: it must hold for all four)
         for (int e = tid; e < QB * 42; e += QT) {
             const int s = e / 42, node = e - 42 * s;
             const QSlot& S = sh.slot[s];
-            if (node < 21 * S.nint) {
-                const int iv = node / 21, q = node - 21 * iv;
-                const double a = iv ? S.a2 : S.a1, b = iv ? S.b2 : S.b1;
-                const double centr = 5.0e-01 * (a + b);
-                const double hlgth = 5.0e-01 * (b - a);
-                const double y = node_eta(centr, hlgth, q);
-                const double t = y / S.xi;
-                sh.ny[s][node][0] = 0.5 * (1.0 + t);
-                sh.ny[s][node][1] = 0.5 * (1.0 - t);
+            if (node >= 21 * S.nint) continue;
+            const int iv = node / 21, q = node - 21 * iv;
+            const double a = iv ? S.a2 : S.a1, b = iv ? S.b2 : S.b1;
+            const double centr = 5.0e-01 * (a + b);
+            const double hlgth = 5.0e-01 * (b - a);
+            const double y = node_eta(centr, hlgth, q);
+            const double t = y / S.xi;
+            const double yy1 = 0.5 * (1.0 + t), yy2 = 0.5 * (1.0 - t);
+            sh.ny[s][node][0] = yy1;
+            sh.ny[s][node][1] = yy2;
+            const double xx1 = S.xx1, xx2 = S.xx2;
+            const bool safe = node_is_safe(xx1, xx2, yy1, yy2);
+            int cls[4];
+            cls[0] = task_class(xx1, yy1, safe);       // dir 0 (K(x,y)), half 0
+            cls[1] = task_class(xx2, yy2, safe);       // dir 0, half 1
+            cls[2] = task_class(yy1, xx1, safe);       // dir 1 (K(y,x)), half 0
+            cls[3] = task_class(yy2, xx2, safe);       // dir 1, half 1
+            int nf = 0, ne = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (!HAS_ERBL && cls[k] == 1) cls[k] = 0;
+                if (cls[k] == 0) sh.hv[s][4 * node + k] = 0.0;
+                nf += (cls[k] == 2);
+                ne += (cls[k] == 1);
             }
-        }
-        __syncthreads();
-        QB_ACC(1);
-
-        // ---------------- C: support classes + compaction ----------------
-        for (int base = 0; base < QB * 168; base += QT) {
-            const int e = base + tid;
-            const int s = (e < QB * 168) ? e / 168 : 0, task = e - 168 * s;
-            const QSlot& S = sh.slot[s];
-            int cls = -1;
-            if (e < QB * 168 && task < 84 * S.nint) {
-                const int node = task >> 2, dir = (task >> 1) & 1, half = task & 1;
-                const double yy1 = sh.ny[s][node][0], yy2 = sh.ny[s][node][1];
-                const double U1 = dir ? yy1 : S.xx1, U2 = dir ? yy2 : S.xx2;
-                const double V1 = dir ? S.xx1 : yy1, V2 = dir ? S.xx2 : yy2;
-                cls = half_class(half ? U2 : U1, half ? V2 : V1, half ? U1 : U2, half ? V1 : V2);
-                if (!HAS_ERBL && cls == 1) cls = 0;
-                if (cls == 0) sh.hv[s][task] = 0.0;
+            int of = nf ? atomicAdd(&sh.nfull, nf) : 0;
+            int oe = ne ? atomicAdd(&sh.nerbl, ne) : 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const unsigned short id = (unsigned short)(s * 168 + 4 * node + k);
+                if (cls[k] == 2) sh.live[of++] = id;
+                if (cls[k] == 1) sh.live[QB * 168 - 1 - (oe++)] = id;
             }
-            const unsigned lt = (1u << lane) - 1u;
-            const unsigned mf = __ballot_sync(0xffffffffu, cls == 2);
-            const unsigned me = __ballot_sync(0xffffffffu, cls == 1);
-            int of = 0, oe = 0;
-            if (lane == 0) {
-                if (mf) of = atomicAdd(&sh.nfull, __popc(mf));
-                if (me) oe = atomicAdd(&sh.nerbl, __popc(me));
-            }
-            of = __shfl_sync(0xffffffffu, of, 0);
-            oe = __shfl_sync(0xffffffffu, oe, 0);
-            if (cls == 2) sh.live[of + __popc(mf & lt)] = (unsigned short)e;
-            if (cls == 1) sh.live[QB * 168 - 1 - (oe + __popc(me & lt))] = (unsigned short)e;
         }
         __syncthreads();
         QB_ACC(2);
