@@ -60,6 +60,9 @@ struct Context {
     cudaEvent_t ev[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
     bool ev_k = false, ev_m = false;
     cudaStream_t side[7] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+    cudaStream_t k1_stream = nullptr;
+    cudaEvent_t k1_fork = nullptr, k1_done = nullptr;
+    bool k1_overlapped = false;
     cudaEvent_t fork = nullptr, join[7] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
 };
 static Context g;
@@ -101,6 +104,9 @@ static int ensure_events()
     for (auto& e : g.ev)
         if (!e) CUDA_OK(cudaEventCreate(&e));
     if (!g.fork) {
+        CUDA_OK(cudaStreamCreateWithFlags(&g.k1_stream, cudaStreamNonBlocking));
+        CUDA_OK(cudaEventCreateWithFlags(&g.k1_fork, cudaEventDisableTiming));
+        CUDA_OK(cudaEventCreate(&g.k1_done));
         CUDA_OK(cudaEventCreateWithFlags(&g.fork, cudaEventDisableTiming));
         for (int k = 0; k < 7; k++) {
             CUDA_OK(cudaStreamCreateWithFlags(&g.side[k], cudaStreamNonBlocking));
@@ -142,8 +148,13 @@ static int make_kernels_impl(int nx, int nxi, const double* xi_host, int grid_ty
     }
     CUDA_OK(cudaMemcpyAsync(g.d_xi, g.xi.data(), sizeof(double) * nxi, cudaMemcpyHostToDevice, st));
 
+    // K1 (fixed quadrature) and K2 (QAGS constants) are independent.  K2's seven persistent launches go
+    // first, K1 runs on its own stream and fills the SMs that K2's draining launches free.
+    const bool overlap_k1 = !getenv("TKB_K1_SERIAL");
     CUDA_OK(cudaEventRecord(g.ev[0], st));
-    if (launch_assemble_fixed(nx, nxi, g.d_xi, grid_type, g.P, g.diag, st)) return 1;
+    if (!overlap_k1) {
+        if (launch_assemble_fixed(nx, nxi, g.d_xi, grid_type, g.P, g.diag, st)) return 1;
+    }
     CUDA_OK(cudaEventRecord(g.ev[1], st));
 
     // QAGS: persistent blocks pulling instances from a counter
@@ -190,6 +201,15 @@ static int make_kernels_impl(int nx, int nxi, const double* xi_host, int grid_ty
         rc = launch_assemble_cst(nx, nxi, g.d_xi, grid_type, (char*)g.scratch + 64, nblocks, counter, g.cst_res,
                                  g.cst_last, g.cst_ifail, st);
     }
+    if (overlap_k1) {
+        CUDA_OK(cudaEventRecord(g.k1_fork, st));                 // after the K2 launches were issued: ordering hint only
+        CUDA_OK(cudaStreamWaitEvent(g.k1_stream, g.ev[0], 0));   // data dependency: the xi upload
+        CUDA_OK(cudaEventRecord(g.ev[5], g.k1_stream));
+        if (launch_assemble_fixed(nx, nxi, g.d_xi, grid_type, g.P, g.diag, g.k1_stream)) return 1;
+        CUDA_OK(cudaEventRecord(g.k1_done, g.k1_stream));
+        CUDA_OK(cudaStreamWaitEvent(st, g.k1_done, 0));
+    }
+    g.k1_overlapped = overlap_k1;
     CUDA_OK(cudaEventRecord(g.ev[2], st));
     g.ev_k = true;
     cudaError_t e = cudaStreamSynchronize(st);
@@ -475,7 +495,11 @@ int tkb_stage_ms(double ms[3])
     float t = 0.f;
     if (g.ev_k) {
         CUDA_OK(cudaEventSynchronize(g.ev[2]));
-        CUDA_OK(cudaEventElapsedTime(&t, g.ev[0], g.ev[1])); ms[0] = t;
+        if (g.k1_overlapped) {     // K1 ran concurrently: its own span, and the whole assembly span for K2
+            CUDA_OK(cudaEventElapsedTime(&t, g.ev[5], g.k1_done)); ms[0] = t;
+        } else {
+            CUDA_OK(cudaEventElapsedTime(&t, g.ev[0], g.ev[1])); ms[0] = t;
+        }
         CUDA_OK(cudaEventElapsedTime(&t, g.ev[1], g.ev[2])); ms[1] = t;
     }
     if (g.ev_m) {
