@@ -9,6 +9,7 @@
 // launches + 2 elementwise launches per matrix type, all xi at once.
 // Matrices are row-major; tcgen05 has no FP64 kind, so this is a register-tiled DFMA kernel
 // (shared-memory staged tiles, 16x16 threads, TxT micro-tile per thread).
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include "tkb_internal.h"
 
@@ -22,6 +23,7 @@ namespace tkb {
     } while (0)
 
 constexpr int GEMM_BK = 16;
+static const bool g_gemm_no_dmma = (getenv("TKB_GEMM_DFMA") != nullptr);     // comparison knob: DFMA kernels only
 
 // C = D + alpha * A B.  Block tile (16 T) x (16 T); thread (ty, tx) owns rows ty + 16 a, cols tx + 16 b.
 // Two shared-memory stages: the global loads of tile k+1 are issued into registers before the
@@ -121,6 +123,125 @@ gemm_kernel(int M, int N, int K, double alpha,
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// FP64 tensor-core GEMM: mma.sync.aligned.m8n8k4.f64 (DMMA; tcgen05 has no FP64 kind, so the legacy
+// warp-level MMA is the Blackwell tensor path for doubles).  Block tile 80 x 80 (divides nx = 80/160/320
+// and 2 nx), 4 warps in a 2 x 2 arrangement, each warp a 40 x 40 sub-tile = 5 x 5 MMA tiles (50
+// accumulator doubles per lane).  Per k-step of 4 a warp loads 5 A and 5 B fragments (one double per lane
+// each) for 25 MMAs = 6400 FMA, so shared-memory traffic is ~6x lower than in the DFMA kernel and one
+// instruction issues 256 FMAs.  Same epilogue (C = D + alpha * A B), same two-stage pipeline.
+// Fragment layout (PTX ISA, m8n8k4 .f64): A: lane holds a[row = lane/4][k = lane%4]; B: lane holds
+// b[k = lane%4][col = lane/4]; C/D: lane holds c[row = lane/4][col = 2*(lane%4) + {0,1}].
+
+__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+constexpr int DM_BT = 80;            // block tile (rows and columns)
+constexpr int DM_WT = 40;            // warp tile
+constexpr int DM_NT = DM_WT / 8;     // MMA tiles per warp-tile side
+constexpr int DM_PAD = 4;            // smem row stride 84 doubles = 8 banks mod 32: the 4 k-rows of a fragment load hit disjoint banks
+
+__global__ void __launch_bounds__(128)
+gemm_dmma_kernel(int M, int N, int K, double alpha,
+                 const double* __restrict__ A, int lda, int64_t strideA,
+                 const double* __restrict__ B, int ldb, int64_t strideB, int bdivB,
+                 const double* __restrict__ D, int ldd, int64_t strideD,
+                 double* __restrict__ C, int ldc, int64_t strideC)
+{
+    __shared__ double As[2][GEMM_BK][DM_BT + DM_PAD];     // As[stage][k][m]
+    __shared__ double Bs[2][GEMM_BK][DM_BT + DM_PAD];     // Bs[stage][k][n]
+    const int b = blockIdx.z;
+    A += (int64_t)b * strideA;
+    B += (int64_t)(b / bdivB) * strideB;
+    C += (int64_t)b * strideC;
+    if (D) D += (int64_t)b * strideD;
+    const int row0 = blockIdx.y * DM_BT, col0 = blockIdx.x * DM_BT;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int wr = (warp >> 1) * DM_WT, wc = (warp & 1) * DM_WT;        // warp tile origin inside the block tile
+    const int fr = lane >> 2, fk = lane & 3;                              // fragment coordinates
+
+    double acc[DM_NT][DM_NT][2];
+#pragma unroll
+    for (int i = 0; i < DM_NT; i++)
+#pragma unroll
+        for (int j = 0; j < DM_NT; j++) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+
+    constexpr int NLD = (DM_BT * GEMM_BK) / 128;          // 10 loads per thread for each operand tile
+    double ra[NLD], rb[NLD];
+    auto load_tile = [&](int k0) {
+#pragma unroll
+        for (int u = 0; u < NLD; u++) {
+            const int e = tid + 128 * u;
+            const int r = e >> 4, kk = e & 15;             // A: 80 rows x 16 k, k fastest (contiguous in memory)
+            const int gr = row0 + r, gk = k0 + kk;
+            ra[u] = (gr < M && gk < K) ? __ldg(A + (int64_t)gr * lda + gk) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < NLD; u++) {
+            const int e = tid + 128 * u;
+            const int kk = e / DM_BT, c = e - kk * DM_BT;  // B: 16 k x 80 cols, cols fastest
+            const int gk = k0 + kk, gc = col0 + c;
+            rb[u] = (gk < K && gc < N) ? __ldg(B + (int64_t)gk * ldb + gc) : 0.0;
+        }
+    };
+    auto store_tile = [&](int st) {
+#pragma unroll
+        for (int u = 0; u < NLD; u++) {
+            const int e = tid + 128 * u;
+            As[st][e & 15][e >> 4] = ra[u];
+        }
+#pragma unroll
+        for (int u = 0; u < NLD; u++) {
+            const int e = tid + 128 * u;
+            const int kk = e / DM_BT;
+            Bs[st][kk][e - kk * DM_BT] = rb[u];
+        }
+    };
+
+    load_tile(0);
+    store_tile(0);
+    __syncthreads();
+    int st = 0;
+    for (int k0 = 0; k0 < K; k0 += GEMM_BK) {
+        const bool more = (k0 + GEMM_BK) < K;
+        if (more) load_tile(k0 + GEMM_BK);
+#pragma unroll
+        for (int k4 = 0; k4 < GEMM_BK; k4 += 4) {
+            double af[DM_NT], bf[DM_NT];
+#pragma unroll
+            for (int i = 0; i < DM_NT; i++) af[i] = As[st][k4 + fk][wr + 8 * i + fr];
+#pragma unroll
+            for (int j = 0; j < DM_NT; j++) bf[j] = Bs[st][k4 + fk][wc + 8 * j + fr];
+#pragma unroll
+            for (int i = 0; i < DM_NT; i++)
+#pragma unroll
+                for (int j = 0; j < DM_NT; j++) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+        if (more) store_tile(st ^ 1);
+        __syncthreads();
+        st ^= 1;
+    }
+#pragma unroll
+    for (int i = 0; i < DM_NT; i++) {
+        const int gr = row0 + wr + 8 * i + fr;
+        if (gr >= M) continue;
+#pragma unroll
+        for (int j = 0; j < DM_NT; j++) {
+            const int gc = col0 + wc + 8 * j + 2 * fk;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                if (gc + h >= N) continue;
+                double v = alpha * acc[i][j][h];
+                if (D) v = D[(int64_t)gr * ldd + gc + h] + v;
+                C[(int64_t)gr * ldc + gc + h] = v;
+            }
+        }
+    }
+}
+
 int launch_gemm(int M, int N, int K, double alpha,
                 const double* A, int lda, int64_t strideA,
                 const double* B, int ldb, int64_t strideB, int bdivB,
@@ -139,7 +260,11 @@ int launch_gemm(int M, int N, int K, double alpha,
         const double* Bb = B + (int64_t)(b0 / bdivB) * strideB;
         const double* Db = D ? D + (int64_t)b0 * strideD : nullptr;
         double* Cb = C + (int64_t)b0 * strideC;
-        if (t5) {
+        if (N >= 40 && !g_gemm_no_dmma) {
+            dim3 grid((N + DM_BT - 1) / DM_BT, (M + DM_BT - 1) / DM_BT, nb);
+            gemm_dmma_kernel<<<grid, 128, 0, st>>>(M, N, K, alpha, Ab, lda, strideA, Bb, ldb, strideB, bdivB, Db, ldd,
+                                                   strideD, Cb, ldc, strideC);
+        } else if (t5) {
             dim3 grid((N + 79) / 80, (M + 79) / 80, nb);
             gemm_kernel<5><<<grid, 256, 0, st>>>(M, N, K, alpha, Ab, lda, strideA, Bb, ldb, strideB, bdivB, Db, ldd,
                                                  strideD, Cb, ldc, strideC);
