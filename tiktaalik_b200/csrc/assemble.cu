@@ -771,6 +771,7 @@ L130:
 
 }  // namespace tkb
 #include "assemble_cst_batched.cuh"
+#include "assemble_cst_replay.cuh"
 namespace tkb {
 
 // One launch per constant c (kernel KID).  instance -> (ixi, i, sub); results go to
@@ -1020,6 +1021,76 @@ int launch_assemble_cst_batched(int n, int nxi, const double* xi_dev, int grid_t
 #endif
     return 0;
 }
+// leader / follower form (assemble_cst_replay.cuh).  Streams: side[0] GG leader, side[1] NS leader,
+// side[2..6] followers (KA1_GG, KV1_GG_nfl, KA1_GG_nfl after the GG leader; KV1_NSm, KV1_NS_nfl after the NS leader).
+constexpr int RP_SLOTS = 16;             // slots per block reserved in the global list area (max over the launches)
+size_t qags_replay_lists_bytes(int nblocks) { return sizeof(QLists) * (size_t)RP_SLOTS * nblocks * 7; }
+size_t qags_replay_log_doubles(int which /*0 NS pair log, 1 unused*/, size_t ninst, int L) { return which == 0 ? ninst * (size_t)L * (4 + 42) : 0; }
+
+template <int KID, int C1, int C2, int C3, bool FOLLOW, int QBv, int QTv>
+static int launch_replay_one(int c, int n, int nxi, const double* xi_dev, int grid_type, QLists* lists, int sms,
+                             unsigned long long* counter, double* cst_res, int* cst_last, int* cst_ifail, double* log,
+                             int* nlog, int L, int rec, int ci, cudaStream_t st)
+{
+    using KS = KernelSet<KID, C1, C2, C3>;
+    const size_t smem = sizeof(QReplayShared<QBv, KS::NKER>);
+    auto kern = assemble_cst_replay_kernel<KID, C1, C2, C3, FOLLOW, QBv, QTv, 2>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
+    const unsigned long long total = (unsigned long long)nxi * n * 3ULL;
+    long long nb = (long long)sms * 2;
+    const long long want = (long long)((total + QBv - 1) / QBv);
+    if (nb > want) nb = want;
+    kern<<<(int)nb, QTv, smem, st>>>(c, n, nxi, xi_dev, grid_type, lists, counter, cst_res, cst_last, cst_ifail, log, nlog,
+                                     L, rec, ci);
+    TKB_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_assemble_cst_replay(int n, int nxi, const double* xi_dev, int grid_type, void* lists, int sms,
+                               unsigned long long* counters /*[7]*/, double* cst_res, int* cst_last, int* cst_ifail,
+                               double* log_ns, double* log_gg, int* nlog_ns, int* nlog_gg, int L,
+                               cudaStream_t st, cudaStream_t* side /*[7]*/, cudaEvent_t fork, cudaEvent_t* join /*[7]*/,
+                               cudaEvent_t* leader_done /*[2]*/)
+{
+    cudaError_t e = cudaMemsetAsync(counters, 0, 7 * sizeof(unsigned long long), st);
+    if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
+    e = cudaEventRecord(fork, st);
+    if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
+    for (int k = 0; k < 7; k++) {
+        e = cudaStreamWaitEvent(side[k], fork, 0);
+        if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
+    }
+    QLists* Lp = (QLists*)lists;
+    const size_t region = (size_t)RP_SLOTS * sms * 2;
+    const int rec_ns = 4 + 42 * 2, rec_gg = 4 + 42 * 3;
+#define RP_ARGS(c) c, n, nxi, xi_dev, grid_type, Lp + region * (c), sms, counters + (c), cst_res, cst_last, cst_ifail
+    // Sharing pays only where the follower's evaluation saving exceeds its (unchanged) bookkeeping cost and
+    // the leader's extra work: measured on C3, KV1_NSm behind KV1_NSp (-19 ms / +4 ms).  The gluon family and
+    // the cheap nfl kernels are bookkeeping-bound as followers, so they run unshared.
+    const int rec_pair = 4 + 42;
+    if (launch_replay_one<K_V1GG, -1, -1, -1, false, 16, 384>(RP_ARGS(3), nullptr, nullptr, 0, 0, 0, side[0])) return 1;
+    if (launch_replay_one<K_NSP, K_NSM, -1, -1, false, 14, 352>(RP_ARGS(0), log_ns, nlog_ns, L, rec_pair, 0, side[1])) return 1;
+    e = cudaEventRecord(leader_done[0], side[1]);
+    if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
+    if (launch_replay_one<K_A1GG, -1, -1, -1, false, 16, 384>(RP_ARGS(4), nullptr, nullptr, 0, 0, 0, side[2])) return 1;
+    e = cudaStreamWaitEvent(side[5], leader_done[0], 0);
+    if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
+    if (launch_replay_one<K_NSM, -1, -1, -1, true, 16, 384>(RP_ARGS(1), log_ns, nlog_ns, L, rec_pair, 0, side[5])) return 1;
+    if (launch_replay_one<K_V1GGN, -1, -1, -1, false, 16, 384>(RP_ARGS(5), nullptr, nullptr, 0, 0, 0, side[3])) return 1;
+    if (launch_replay_one<K_A1GGN, -1, -1, -1, false, 16, 384>(RP_ARGS(6), nullptr, nullptr, 0, 0, 0, side[4])) return 1;
+    if (launch_replay_one<K_NSN, -1, -1, -1, false, 16, 384>(RP_ARGS(2), nullptr, nullptr, 0, 0, 0, side[6])) return 1;
+    (void)log_gg; (void)nlog_gg; (void)rec_ns; (void)rec_gg; (void)leader_done;
+#undef RP_ARGS
+    for (int k = 0; k < 7; k++) {
+        e = cudaEventRecord(join[k], side[k]);
+        if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
+        e = cudaStreamWaitEvent(st, join[k], 0);
+        if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
+    }
+    return 0;
+}
+
 size_t qags_batched_bytes_per_block() { return qags_lists_bytes(); }
 int qags_batched_instances_per_block() { return QB; }
 int qags_batched_blocks_per_sm() { return QBLOCKS_PER_SM; }

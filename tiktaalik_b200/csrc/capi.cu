@@ -60,6 +60,9 @@ struct Context {
     cudaEvent_t ev[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
     bool ev_k = false, ev_m = false;
     cudaStream_t side[7] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+    cudaEvent_t leader_done[2] = { nullptr, nullptr };
+    double* qlog = nullptr;     // leader logs (NS then GG) + step counts, kept across calls
+    size_t qlog_bytes = 0;
     cudaStream_t k1_stream = nullptr;
     cudaEvent_t k1_fork = nullptr, k1_done = nullptr;
     bool k1_overlapped = false;
@@ -108,6 +111,8 @@ static int ensure_events()
         CUDA_OK(cudaEventCreateWithFlags(&g.k1_fork, cudaEventDisableTiming));
         CUDA_OK(cudaEventCreate(&g.k1_done));
         CUDA_OK(cudaEventCreateWithFlags(&g.fork, cudaEventDisableTiming));
+        CUDA_OK(cudaEventCreateWithFlags(&g.leader_done[0], cudaEventDisableTiming));
+        CUDA_OK(cudaEventCreateWithFlags(&g.leader_done[1], cudaEventDisableTiming));
         for (int k = 0; k < 7; k++) {
             CUDA_OK(cudaStreamCreateWithFlags(&g.side[k], cudaStreamNonBlocking));
             CUDA_OK(cudaEventCreateWithFlags(&g.join[k], cudaEventDisableTiming));
@@ -167,10 +172,43 @@ static int make_kernels_impl(int nx, int nxi, const double* xi_host, int grid_ty
     int nblocks = sms * 8;        // more than fit at once: the spare blocks start as others drain
     if (const char* env = getenv("TKB_K2_BLOCKS_PER_SM")) { const int v = atoi(env); if (v > 0) nblocks = sms * v; }   // tuning knob
     if ((long long)nblocks > want) nblocks = (int)want;
-    // K2 form: batched (default) or one instance per warp (TKB_K2_MODE=warp, kept for comparison)
+    // K2 form: leader/follower replay (default), batched without sharing (TKB_K2_MODE=batched), or one
+    // instance per warp (TKB_K2_MODE=warp); the last two are kept for comparison
     const char* mode = getenv("TKB_K2_MODE");
-    const bool batched = !(mode && mode[0] == 'w');
+    const bool warpmode = (mode && mode[0] == 'w');
+    const bool replay = !(mode && (mode[0] == 'w' || mode[0] == 'b'));
+    const bool batched = !warpmode;
     int rc = 0;
+    if (replay) {
+        const size_t ninst = (size_t)rows * 3;
+        // log depth: as many steps as fit a memory budget (instances with longer paths leave the log there)
+        size_t budget = (size_t)6 << 30;
+        if (const char* env = getenv("TKB_K2_LOG_GB")) budget = (size_t)atof(env) * ((size_t)1 << 30);
+        long long Lmax = (long long)(budget / (8.0 * (double)ninst * 46.0));
+        int L = (int)(Lmax > 48 ? 48 : (Lmax < 4 ? 4 : Lmax));
+        const size_t lists_b = qags_replay_lists_bytes(sms * 2);
+        const size_t need = lists_b + 64;
+        if (g.scratch_bytes < need) {
+            if (g.scratch) cudaFree(g.scratch);
+            g.scratch = nullptr;
+            g.scratch_bytes = 0;
+            CUDA_OK(cudaMalloc(&g.scratch, need));
+            g.scratch_bytes = need;
+        }
+        const size_t dn = qags_replay_log_doubles(0, ninst, L), dg = qags_replay_log_doubles(1, ninst, L);
+        const size_t lneed = (dn + dg) * sizeof(double) + 2 * ninst * sizeof(int);
+        if (g.qlog_bytes < lneed) {
+            if (g.qlog) cudaFree(g.qlog);
+            g.qlog = nullptr;
+            g.qlog_bytes = 0;
+            CUDA_OK(cudaMalloc(&g.qlog, lneed));
+            g.qlog_bytes = lneed;
+        }
+        int* nl = (int*)(g.qlog + dn + dg);
+        rc = launch_assemble_cst_replay(nx, nxi, g.d_xi, grid_type, (char*)g.scratch + 64, sms,
+                                        (unsigned long long*)g.scratch, g.cst_res, g.cst_last, g.cst_ifail,
+                                        g.qlog, g.qlog + dn, nl, nl + ninst, L, st, g.side, g.fork, g.join, g.leader_done);
+    } else
     if (batched) {
         const int qb = qags_batched_instances_per_block();
         int nb = sms * qags_batched_blocks_per_sm();
@@ -457,8 +495,9 @@ int tkb_free(void)
     free_kernels();
     if (g.scratch) cudaFree(g.scratch);
     if (g.ws) cudaFree(g.ws);
-    g.scratch = nullptr; g.ws = nullptr;
-    g.scratch_bytes = g.ws_bytes = 0;
+    if (g.qlog) cudaFree(g.qlog);
+    g.scratch = nullptr; g.ws = nullptr; g.qlog = nullptr;
+    g.scratch_bytes = g.ws_bytes = g.qlog_bytes = 0;
     return 0;
 }
 

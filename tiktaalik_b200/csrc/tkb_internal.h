@@ -21,6 +21,13 @@ int launch_assemble_cst(int n, int nxi, const double* xi_dev, int grid_type, voi
 int launch_assemble_cst_batched(int n, int nxi, const double* xi_dev, int grid_type, void* lists, int nblocks,
                                 unsigned long long* counters, double* cst_res, int* cst_last, int* cst_ifail,
                                 cudaStream_t st, cudaStream_t* side, cudaEvent_t fork, cudaEvent_t* join);
+size_t qags_replay_lists_bytes(int nblocks);
+size_t qags_replay_log_doubles(int which, size_t ninst, int L);
+int launch_assemble_cst_replay(int n, int nxi, const double* xi_dev, int grid_type, void* lists, int sms,
+                               unsigned long long* counters, double* cst_res, int* cst_last, int* cst_ifail,
+                               double* log_ns, double* log_gg, int* nlog_ns, int* nlog_gg, int L,
+                               cudaStream_t st, cudaStream_t* side, cudaEvent_t fork, cudaEvent_t* join,
+                               cudaEvent_t* leader_done);
 size_t qags_batched_bytes_per_block();
 int qags_batched_instances_per_block();
 int qags_batched_blocks_per_sm();
