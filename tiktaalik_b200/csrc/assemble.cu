@@ -328,6 +328,72 @@ L90:
     ermax = elist[maxerr];
 }
 
+// The same ordering update with the two linear scans of qsort_ replaced by galloping + binary searches and
+// block shifts.  The bottom scan of qsort_ walks, on average, a third of the list with two dependent loads
+// and an FP64 compare per entry; on the long bisection paths of the plus-prescription constants (hundreds of
+// intervals) that made the ordering update the largest part of the bookkeeping time.  Both scans test a
+// predicate that is monotone along a list sorted by decreasing error estimate, which qsort_ maintains as
+// long as no estimate is a NaN (the caller falls back to qsort_ for good once it has seen one); the first
+// index where the predicate flips is then the same whichever way it is searched, ties included, so the
+// resulting list, maxerr and nrmax are those of qsort_.
+template <typename DL, typename IL>
+static __device__ __noinline__ void qsort_bs_(int limit, int last, int& maxerr, double& ermax, DL elist, IL iord, int& nrmax)
+{
+    if (last <= 2) {
+        iord[1] = 1;
+        iord[2] = 2;
+        maxerr = iord[nrmax];
+        ermax = elist[maxerr];
+        return;
+    }
+    const double errmax = elist[maxerr];
+    {
+        const int ntrip = nrmax - 1;
+        for (int i = 1; i <= ntrip; i++) {
+            const int isucc = iord[nrmax - 1];
+            if (errmax <= elist[isucc]) break;
+            iord[nrmax] = isucc;
+            nrmax = nrmax - 1;
+        }
+    }
+    int jupbn = last;
+    if (last > (limit / 2 + 2)) jupbn = limit + 3 - last;
+    const double errmin = elist[last];
+    const int jbnd = jupbn - 1, ibeg = nrmax + 1;
+    // i = first index in [ibeg, jbnd] with errmax >= elist[iord[i]], jbnd + 1 if there is none
+    int lo = ibeg, hi = jbnd + 1;
+    for (int p = ibeg, step = 1; p <= jbnd; p += step, step <<= 1) {
+        if (errmax >= elist[iord[p]]) { hi = p; break; }
+        lo = p + 1;
+    }
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (errmax >= elist[iord[mid]]) hi = mid; else lo = mid + 1;
+    }
+    const int i = lo;
+    for (int t = ibeg; t < i; t++) iord[t - 1] = iord[t];
+    if (i > jbnd) {
+        iord[jbnd] = maxerr;
+        iord[jupbn] = last;
+    } else {
+        iord[i - 1] = maxerr;
+        // k = largest index in [i, jbnd] with errmin < elist[iord[k]], i - 1 if there is none
+        int klo = i - 1, khi = jbnd + 1;
+        for (int p = jbnd, step = 1; p >= i; p -= step, step <<= 1) {
+            if (errmin < elist[iord[p]]) { klo = p; break; }
+            khi = p;
+        }
+        while (khi - klo > 1) {
+            const int mid = (klo + khi) >> 1;
+            if (errmin < elist[iord[mid]]) klo = mid; else khi = mid;
+        }
+        for (int t = jbnd; t > klo; t--) iord[t + 1] = iord[t];
+        iord[klo + 1] = last;
+    }
+    maxerr = iord[nrmax];
+    ermax = elist[maxerr];
+}
+
 // integration.f90:732-904
 static __device__ __noinline__ void qextr_(int& n, double* epstab, double& result, double& abserr, double* res3la, int& nres)
 {
@@ -772,6 +838,7 @@ L130:
 }  // namespace tkb
 #include "assemble_cst_batched.cuh"
 #include "assemble_cst_replay.cuh"
+#include "assemble_cst_pipe.cuh"
 namespace tkb {
 
 // One launch per constant c (kernel KID).  instance -> (ixi, i, sub); results go to
@@ -1047,6 +1114,37 @@ static int launch_replay_one(int c, int n, int nxi, const double* xi_dev, int gr
     return 0;
 }
 
+#ifndef TKB_QPG
+#define TKB_QPG 16
+#endif
+#ifndef TKB_QPT
+#define TKB_QPT 768
+#endif
+#ifndef TKB_QPBPS
+#define TKB_QPBPS 1
+#endif
+#ifndef TKB_QPBW
+#define TKB_QPBW 2
+#endif
+template <int KID>
+static int launch_pipe_one(int c, int n, int nxi, const double* xi_dev, int grid_type, QLists* lists, int sms,
+                           unsigned long long* counter, double* cst_res, int* cst_last, int* cst_ifail, cudaStream_t st)
+{
+    constexpr int QG = TKB_QPG, NT = TKB_QPT, BPS = TKB_QPBPS, NBW = TKB_QPBW;
+    static_assert(2 * QG * BPS <= RP_SLOTS * 2, "global list area reserved per SM");
+    const size_t smem = sizeof(QPipeShared<QG>);
+    auto kern = assemble_cst_pipe_kernel<KID, QG, NT, BPS, NBW>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
+    const unsigned long long total = (unsigned long long)nxi * n * 3ULL;
+    long long nb = (long long)sms * BPS;
+    const long long want = (long long)((total + 2 * QG - 1) / (2 * QG));
+    if (nb > want) nb = want;
+    kern<<<(int)nb, NT, smem, st>>>(c, n, nxi, xi_dev, grid_type, lists, counter, cst_res, cst_last, cst_ifail);
+    TKB_LAUNCH_CHECK();
+    return 0;
+}
+
 int launch_assemble_cst_replay(int n, int nxi, const double* xi_dev, int grid_type, void* lists, int sms,
                                unsigned long long* counters /*[7]*/, double* cst_res, int* cst_last, int* cst_ifail,
                                double* log_ns, double* log_gg, int* nlog_ns, int* nlog_gg, int L,
@@ -1069,17 +1167,25 @@ int launch_assemble_cst_replay(int n, int nxi, const double* xi_dev, int grid_ty
     // the leader's extra work: measured on C3, KV1_NSm behind KV1_NSp (-19 ms / +4 ms).  The gluon family and
     // the cheap nfl kernels are bookkeeping-bound as followers, so they run unshared.
     const int rec_pair = 4 + 42;
-    if (launch_replay_one<K_V1GG, -1, -1, -1, false, 16, 384>(RP_ARGS(3), nullptr, nullptr, 0, 0, 0, side[0])) return 1;
+    // unshared constants: role-split pipeline (assemble_cst_pipe.cuh) unless TKB_K2_MODE=replay asks for the
+    // lock-step form
+    const char* mode_ = getenv("TKB_K2_MODE");
+    const bool pipe = !(mode_ && mode_[0] == 'r');
+#define RP_PLAIN(c, KID, strm)                                                                                        \
+    if (pipe ? launch_pipe_one<KID>(RP_ARGS(c), strm)                                                                  \
+             : launch_replay_one<KID, -1, -1, -1, false, 16, 384>(RP_ARGS(c), nullptr, nullptr, 0, 0, 0, strm)) return 1;
+    RP_PLAIN(3, K_V1GG, side[0])
     if (launch_replay_one<K_NSP, K_NSM, -1, -1, false, 14, 352>(RP_ARGS(0), log_ns, nlog_ns, L, rec_pair, 0, side[1])) return 1;
     e = cudaEventRecord(leader_done[0], side[1]);
     if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
-    if (launch_replay_one<K_A1GG, -1, -1, -1, false, 16, 384>(RP_ARGS(4), nullptr, nullptr, 0, 0, 0, side[2])) return 1;
+    RP_PLAIN(4, K_A1GG, side[2])
     e = cudaStreamWaitEvent(side[5], leader_done[0], 0);
     if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
     if (launch_replay_one<K_NSM, -1, -1, -1, true, 16, 384>(RP_ARGS(1), log_ns, nlog_ns, L, rec_pair, 0, side[5])) return 1;
-    if (launch_replay_one<K_V1GGN, -1, -1, -1, false, 16, 384>(RP_ARGS(5), nullptr, nullptr, 0, 0, 0, side[3])) return 1;
-    if (launch_replay_one<K_A1GGN, -1, -1, -1, false, 16, 384>(RP_ARGS(6), nullptr, nullptr, 0, 0, 0, side[4])) return 1;
-    if (launch_replay_one<K_NSN, -1, -1, -1, false, 16, 384>(RP_ARGS(2), nullptr, nullptr, 0, 0, 0, side[6])) return 1;
+    RP_PLAIN(5, K_V1GGN, side[3])
+    RP_PLAIN(6, K_A1GGN, side[4])
+    RP_PLAIN(2, K_NSN, side[6])
+#undef RP_PLAIN
     (void)log_gg; (void)nlog_gg; (void)rec_ns; (void)rec_gg; (void)leader_done;
 #undef RP_ARGS
     for (int k = 0; k < 7; k++) {
@@ -1088,6 +1194,18 @@ int launch_assemble_cst_replay(int n, int nxi, const double* xi_dev, int grid_ty
         e = cudaStreamWaitEvent(st, join[k], 0);
         if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
     }
+#ifdef TKB_K2_STATS
+    {
+        cudaStreamSynchronize(st);
+        unsigned long long h[16];
+        cudaMemcpyFromSymbol(h, g_k2stats, sizeof h);
+        fprintf(stderr, "K2 S-phase stats: qsort %.0f cyc x %llu | qextr %.0f cyc x %llu | qk21_reduce %.0f cyc | qags_step (incl. qsort/qextr) %.0f cyc x %llu\n",
+                h[9] ? (double)h[8] / h[9] : 0.0, h[9], h[11] ? (double)h[10] / h[11] : 0.0, h[11],
+                h[14] ? (double)h[12] / h[14] : 0.0, h[14] ? (double)h[13] / h[14] : 0.0, h[14]);
+        unsigned long long z[16] = { 0 };
+        cudaMemcpyToSymbol(g_k2stats, z, sizeof z);
+    }
+#endif
     return 0;
 }
 

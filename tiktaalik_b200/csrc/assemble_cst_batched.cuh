@@ -41,6 +41,7 @@ struct QSlot {                       // scalar QUADPACK state of one instance (i
     unsigned long long inst;
     int maxerr, nrmax, nres, numrl2, ktmin, iroff1, iroff2, iroff3, ierro, ifail, ksgn, last;
     int extrap, noext;
+    int nanl;                        // an error estimate was a NaN: the ordered list may be unsorted (see qsort_bs_)
     int nint;                        // 0 idle, 1 first qk21 pending, 2 bisection pending
 };
 
@@ -85,6 +86,7 @@ static __device__ __noinline__ int qags_first(QSlot& S, QHead& H, QLists& L, con
     const double dres = fabs(result);
     const double errbnd = fmax2(epsabs, epsrel * dres);
     S.last = 1;
+    S.nanl = 0;
     rlist[1] = result;
     elist[1] = abserr;
     iord[1] = 1;
@@ -194,7 +196,15 @@ L15:
         elist[maxerr] = error2;
         elist[last] = error1;
     }
-    qsort_(limit, last, maxerr, errmax, elist, iord, nrmax);
+#ifdef TKB_K2_STATS
+    long long tq0_ = clock64();
+#endif
+    if (!(error1 == error1) || !(error2 == error2)) S.nanl = 1;
+    if (S.nanl) qsort_(limit, last, maxerr, errmax, elist, iord, nrmax);
+    else qsort_bs_(limit, last, maxerr, errmax, elist, iord, nrmax);
+#ifdef TKB_K2_STATS
+    atomicAdd(&g_k2stats[8], (unsigned long long)(clock64() - tq0_)); atomicAdd(&g_k2stats[9], 1ULL);
+#endif
     if (errsum <= errbnd) { status = 2; goto Lend; }
     if (ifail != 0) { status = 1; goto Lend; }
     if (last == 2) goto L80;
@@ -219,7 +229,13 @@ L40:
     }
     numrl2 = numrl2 + 1;
     rlist2[numrl2] = area;
+#ifdef TKB_K2_STATS
+    tq0_ = clock64();
+#endif
     qextr_(numrl2, rlist2, reseps, abseps, S.res3la, nres);
+#ifdef TKB_K2_STATS
+    atomicAdd(&g_k2stats[10], (unsigned long long)(clock64() - tq0_)); atomicAdd(&g_k2stats[11], 1ULL);
+#endif
     ktmin = ktmin + 1;
     if (ktmin > 5 && abserr < 1.0e-03 * errsum) ifail = 5;
     if (abseps < abserr) {

@@ -1,0 +1,260 @@
+// assemble_cst_pipe.cuh -- K2 with the QUADPACK bookkeeping taken off the evaluators' critical path.
+// Included by assemble.cu after assemble_cst_batched.cuh (whose QSlot / QHead / qags_* helpers it reuses).
+//
+// In the lock-step form (assemble_cst_batched.cuh) every round ends in a bookkeeping phase in which one
+// lane pair per instance runs QUADPACK's scalar code (qk21 sums, list update, qsort, epsilon table: about
+// 15-25 k cycles of dependent FP64 latency, the maximum over the block's instances) while all other threads
+// wait at the barrier: ncu showed 4.1 of 11.9 warp-cycles per issued instruction spent in barrier stalls.
+// Here a block is split by role:
+//   * warp 0 is the BOOKKEEPER.  It owns two groups of QG instances, one lane pair per instance;
+//   * all other warps are EVALUATORS.  They alternate between the groups: node arguments, support classes,
+//     live half kernels, K(x,y) - K(y,x) of group g, then the same for group g^1.
+// While the evaluators work on group g^1 the bookkeeper consumes the values of group g and posts its next
+// requests, so the evaluators never wait for scalar code unless one bookkeeping step outlasts a whole
+// evaluation phase.  The hand-over uses four named barriers (bar.arrive by the producer, bar.sync by the
+// consumer) and a fifth one among the evaluators.
+// The arithmetic and the control flow of every instance are those of the lock-step form, hence results,
+// `last` and `ifail` stay bit-identical to it and to the oracle.
+#pragma once
+
+namespace tkb {
+
+template <int QG>
+struct QPipeShared {
+    QSlot slot[2 * QG];
+    QHead head[2 * QG];
+    double ny[2 * QG][42][2];
+    double hv[2 * QG][168];
+    double fv[2 * QG][42];
+    unsigned short live[2][QG * 168];
+    int nfull[2], nerbl[2], done[2];
+};
+
+enum { QP_BAR_REQ0 = 1, QP_BAR_REQ1 = 2, QP_BAR_VAL0 = 3, QP_BAR_VAL1 = 4, QP_BAR_EV = 5 };
+
+// barrier ids are immediates so that ptxas reserves only the barriers in use (a register id reserves all 16)
+template <int ID>
+__device__ __forceinline__ void qp_bar_sync_i(int count)
+{
+    asm volatile("bar.sync %0, %1;" ::"n"(ID), "r"(count) : "memory");
+}
+template <int ID>
+__device__ __forceinline__ void qp_bar_arrive_i(int count)
+{
+    asm volatile("bar.arrive %0, %1;" ::"n"(ID), "r"(count) : "memory");
+}
+__device__ __forceinline__ void qp_bar_sync(int id, int count)
+{
+    switch (id) {
+    case 1: qp_bar_sync_i<1>(count); break;
+    case 2: qp_bar_sync_i<2>(count); break;
+    case 3: qp_bar_sync_i<3>(count); break;
+    case 4: qp_bar_sync_i<4>(count); break;
+    default: qp_bar_sync_i<5>(count); break;
+    }
+}
+__device__ __forceinline__ void qp_bar_arrive(int id, int count)
+{
+    switch (id) {
+    case 1: qp_bar_arrive_i<1>(count); break;
+    case 2: qp_bar_arrive_i<2>(count); break;
+    case 3: qp_bar_arrive_i<3>(count); break;
+    default: qp_bar_arrive_i<4>(count); break;
+    }
+}
+
+template <int KID, int QG, int NT, int BPS, int NBW>
+__global__ void __launch_bounds__(NT, BPS)
+assemble_cst_pipe_kernel(int c, int n, int nxi, const double* __restrict__ xi_arr, int grid_type,
+                         QLists* __restrict__ lists, unsigned long long* __restrict__ counter,
+                         double* __restrict__ cst_res, int* __restrict__ cst_last, int* __restrict__ cst_ifail)
+{
+    static_assert(2 * QG <= 32, "one lane pair per instance of a group in the bookkeeping warp");
+    static_assert(NBW == 1 || NBW == 2, "one bookkeeping warp for both groups, or one per group");
+    constexpr int NE = NT - 32 * NBW;                 // evaluator threads
+    constexpr int NRQ = NE + 32;                      // participants of a hand-over barrier: one bookkeeping warp + evaluators
+    constexpr bool HAS_ERBL = (KID != K_NSN);
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    QPipeShared<QG>& sh = *reinterpret_cast<QPipeShared<QG>*>(smem_raw);
+    const int tid = threadIdx.x;
+    const unsigned long long total = (unsigned long long)nxi * n * 3ULL;
+    if (tid < 2 * QG) sh.slot[tid].nint = 0;
+    if (tid < 2) { sh.nfull[tid] = 0; sh.nerbl[tid] = 0; sh.done[tid] = 0; }
+    __syncthreads();
+
+    if (tid < 32 * NBW) {
+        // ======================= bookkeeper =======================
+        const int lane = tid & 31, part = lane & 1;
+        const bool mine = (lane >> 1) < QG;
+        bool exhausted = false;
+        int alive = (NBW == 2) ? (1 << (tid >> 5)) : 3, g = (NBW == 2) ? (tid >> 5) : 0;
+        for (int round = 0; alive != 0; round++, g ^= (NBW == 2 ? 0 : 1)) {
+            if (!((alive >> g) & 1)) continue;
+            if (round >= (NBW == 2 ? 1 : 2)) qp_bar_sync(QP_BAR_VAL0 + g, NRQ);      // the first round(s) only pull instances
+            const int myslot = g * QG + (mine ? (lane >> 1) : 0);
+            QSlot& S = sh.slot[myslot];
+            QLists* myL = lists + (size_t)blockIdx.x * (2 * QG) + myslot;
+            const int nint0 = mine ? S.nint : 0;
+            double r_ = 0, e_ = 0, ra_ = 0, rc_ = 0;
+            if (nint0 == 2) qk21_reduce(sh.fv[myslot] + 21 * part, part ? S.a2 : S.a1, part ? S.b2 : S.b1, r_, e_, ra_, rc_);
+            const double area2 = __shfl_down_sync(0xffffffffu, r_, 1);
+            const double error2 = __shfl_down_sync(0xffffffffu, e_, 1);
+            const double defab2 = __shfl_down_sync(0xffffffffu, rc_, 1);
+            if (mine && part == 0) {
+                int state = QS_DONE;
+                if (nint0 == 1) {
+                    state = qags_first(S, sh.head[myslot], *myL, sh.fv[myslot]);
+                    if (state == QS_CONTINUE) {
+                        S.a1 = S.a;
+                        S.b1 = 5.0e-01 * (S.a + S.b);
+                        S.a2 = S.b1;
+                        S.b2 = S.b;
+                        S.erlast = S.errmax;
+                        S.nint = 2;
+                    }
+                } else if (nint0 == 2) {
+                    state = qags_step(S, sh.head[myslot], *myL, r_, e_, rc_, area2, error2, defab2);
+                }
+                if (state == QS_DONE) {
+                    if (nint0 != 0) {
+                        const unsigned long long row = S.inst / 3ULL;
+                        const size_t idx = ((size_t)row * 7 + (size_t)c) * 3 + (size_t)(S.inst % 3ULL);
+                        cst_res[idx] = S.result;
+                        cst_last[idx] = S.last;
+                        cst_ifail[idx] = S.ifail;
+                        S.nint = 0;
+                    }
+                    if (!exhausted) {
+                        const unsigned long long inst = atomicAdd(counter, 1ULL);
+                        if (inst >= total) exhausted = true;
+                        else {
+                            const int sub = (int)(inst % 3ULL);
+                            const unsigned long long row = inst / 3ULL;
+                            const int i = (int)(row % (unsigned long long)n) + 1;
+                            const int ixi = (int)(row / (unsigned long long)n);
+                            const double xi = xi_arr[ixi];
+                            const double x = grid_node(i, n, xi, grid_type);
+                            const double eps = 1e-15;                        // integration.f90:56-63
+                            const double ymin = -1.0 + eps, ymax = 1.0 - eps;
+                            double a, b;
+                            if (sub == 0) { a = ymin; b = -fabs(x) - eps; }
+                            else if (sub == 1) { a = -fabs(x) + eps; b = fabs(x) - eps; }
+                            else { a = fabs(x) + eps; b = ymax; }
+                            S.inst = inst; S.x = x; S.xi = xi; S.a = a; S.b = b;
+                            S.xx1 = 0.5 * (1.0 + x / xi);
+                            S.xx2 = 0.5 * (1.0 - x / xi);
+                            S.a1 = a; S.b1 = b; S.a2 = a; S.b2 = b;
+                            S.nint = 1;
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            const unsigned act = __ballot_sync(0xffffffffu, mine && part == 0 && S.nint != 0);
+            if (lane == 0) {
+                sh.nfull[g] = 0;
+                sh.nerbl[g] = 0;
+                if (act == 0u) sh.done[g] = 1;
+            }
+            if (act == 0u) alive &= ~(1 << g);
+            __syncwarp();
+            qp_bar_arrive(QP_BAR_REQ0 + g, NRQ);
+        }
+        return;
+    }
+
+    // ======================= evaluators =======================
+    const int etid = tid - 32 * NBW;
+    int alive = 3;
+    for (int g = 0; alive != 0; g ^= 1) {
+        if (!((alive >> g) & 1)) continue;
+        qp_bar_sync(QP_BAR_REQ0 + g, NRQ);
+        if (*(volatile int*)&sh.done[g]) { alive &= ~(1 << g); continue; }
+        unsigned short* live = sh.live[g];
+
+        // ---- N + C: node arguments, support classes, compaction (see assemble_cst_batched.cuh) ----
+        for (int e = etid; e < QG * 42; e += NE) {
+            const int s = g * QG + e / 42, node = e % 42;
+            const QSlot& S = sh.slot[s];
+            if (node >= 21 * S.nint) continue;
+            const int iv = node / 21, q = node - 21 * iv;
+            const double a = iv ? S.a2 : S.a1, b = iv ? S.b2 : S.b1;
+            const double centr = 5.0e-01 * (a + b);
+            const double hlgth = 5.0e-01 * (b - a);
+            const double y = node_eta(centr, hlgth, q);
+            const double t = y / S.xi;
+            const double yy1 = 0.5 * (1.0 + t), yy2 = 0.5 * (1.0 - t);
+            sh.ny[s][node][0] = yy1;
+            sh.ny[s][node][1] = yy2;
+            const double xx1 = S.xx1, xx2 = S.xx2;
+            const bool safe = node_is_safe(xx1, xx2, yy1, yy2);
+            int cls[4];
+            cls[0] = task_class(xx1, yy1, safe);       // dir 0 (K(x,y)), half 0
+            cls[1] = task_class(xx2, yy2, safe);       // dir 0, half 1
+            cls[2] = task_class(yy1, xx1, safe);       // dir 1 (K(y,x)), half 0
+            cls[3] = task_class(yy2, xx2, safe);       // dir 1, half 1
+            int nf = 0, ne = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (!HAS_ERBL && cls[k] == 1) cls[k] = 0;
+                if (cls[k] == 0) sh.hv[s][4 * node + k] = 0.0;
+                nf += (cls[k] == 2);
+                ne += (cls[k] == 1);
+            }
+            int of = nf ? atomicAdd(&sh.nfull[g], nf) : 0;
+            int oe = ne ? atomicAdd(&sh.nerbl[g], ne) : 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const unsigned short id = (unsigned short)((s - g * QG) * 168 + 4 * node + k);
+                if (cls[k] == 2) live[of++] = id;
+                if (cls[k] == 1) live[QG * 168 - 1 - (oe++)] = id;
+            }
+        }
+        qp_bar_sync(QP_BAR_EV, NE);
+
+        // ---- E: evaluate the live half kernels ----
+        const int nfull = *(volatile int*)&sh.nfull[g], nerbl = *(volatile int*)&sh.nerbl[g];
+        for (int idx = etid; idx < nfull; idx += NE) {
+            const int e = live[idx];
+            const int sl = e / 168, task = e - 168 * sl, s = g * QG + sl;
+            const QSlot& S = sh.slot[s];
+            const int node = task >> 2, dir = (task >> 1) & 1, half = task & 1;
+            const double yy1 = sh.ny[s][node][0], yy2 = sh.ny[s][node][1];
+            const double U1 = dir ? yy1 : S.xx1, U2 = dir ? yy2 : S.xx2;
+            const double V1 = dir ? S.xx1 : yy1, V2 = dir ? S.xx2 : yy2;
+            double out[NKERN];
+            eval_half<bit(KID), true>(half ? U2 : U1, half ? V2 : V1, half ? U1 : U2, half ? V1 : V2, out);
+            sh.hv[s][task] = out[KID];
+        }
+        if (HAS_ERBL) {
+            for (int idx = etid; idx < nerbl; idx += NE) {
+                const int e = live[QG * 168 - 1 - idx];
+                const int sl = e / 168, task = e - 168 * sl, s = g * QG + sl;
+                const QSlot& S = sh.slot[s];
+                const int node = task >> 2, dir = (task >> 1) & 1, half = task & 1;
+                const double yy1 = sh.ny[s][node][0], yy2 = sh.ny[s][node][1];
+                const double U1 = dir ? yy1 : S.xx1, U2 = dir ? yy2 : S.xx2;
+                const double V1 = dir ? S.xx1 : yy1, V2 = dir ? S.xx2 : yy2;
+                double out[NKERN];
+                eval_half<bit(KID), false>(half ? U2 : U1, half ? V2 : V1, half ? U1 : U2, half ? V1 : V2, out);
+                sh.hv[s][task] = out[KID];
+            }
+        }
+        qp_bar_sync(QP_BAR_EV, NE);
+
+        // ---- K: K(x,y,xi) - K(y,x,xi) per node ----
+        for (int e = etid; e < QG * 42; e += NE) {
+            const int s = g * QG + e / 42, node = e % 42;
+            const QSlot& S = sh.slot[s];
+            if (node < 21 * S.nint) {
+                const double* h = sh.hv[s] + 4 * node;
+                const double Kxy = combine_halves<KID>(h[0], h[1], S.xi);
+                const double Kyx = combine_halves<KID>(h[2], h[3], S.xi);
+                sh.fv[s][node] = Kxy - Kyx;
+            }
+        }
+        qp_bar_arrive(QP_BAR_VAL0 + g, NRQ);
+    }
+}
+
+}  // namespace tkb

@@ -83,7 +83,13 @@ assemble_cst_replay_kernel(int c, int n, int nxi, const double* __restrict__ xi_
                 // (a) consume the values of the current request
                 const int nint0 = (mine && sh.have[myslot]) ? S.nint : 0;
                 double r_ = 0, e_ = 0, ra_ = 0, rc_ = 0;
+#ifdef TKB_K2_STATS
+                long long ts0_ = clock64();
+#endif
                 if (nint0 == 2) qk21_reduce(sh.fv[myslot][0] + 21 * part, part ? S.a2 : S.a1, part ? S.b2 : S.b1, r_, e_, ra_, rc_);
+#ifdef TKB_K2_STATS
+                if (nint0 == 2 && part == 0) { atomicAdd(&g_k2stats[12], (unsigned long long)(clock64() - ts0_)); ts0_ = clock64(); }
+#endif
                 const double area2 = __shfl_down_sync(0xffffffffu, r_, 1);
                 const double error2 = __shfl_down_sync(0xffffffffu, e_, 1);
                 const double defab2 = __shfl_down_sync(0xffffffffu, rc_, 1);
@@ -101,6 +107,9 @@ assemble_cst_replay_kernel(int c, int n, int nxi, const double* __restrict__ xi_
                         }
                     } else if (nint0 == 2) {
                         state = qags_step(S, sh.head[myslot], *myL, r_, e_, rc_, area2, error2, defab2);
+#ifdef TKB_K2_STATS
+                        atomicAdd(&g_k2stats[13], (unsigned long long)(clock64() - ts0_)); atomicAdd(&g_k2stats[14], 1ULL);
+#endif
                     }
                     sh.have[myslot] = 0;
                     if (state == QS_DONE) {
