@@ -26,8 +26,9 @@ struct QPipeShared {
     double ny[2 * QG][42][2];
     double hv[2 * QG][168];
     double fv[2 * QG][42];
-    unsigned short live[2][QG * 168];
-    int nfull[2], nerbl[2], done[2];
+    double pre[2 * QG][2][PRE_N];       // per instance and half: one-argument transcendental values (eval_half, FIX)
+    unsigned short live[2][2][QG * 84]; // per group and direction: full tasks from the front, erbl-only from the back
+    int nfull[2][2], nerbl[2][2], done[2];
 };
 
 enum { QP_BAR_REQ0 = 1, QP_BAR_REQ1 = 2, QP_BAR_VAL0 = 3, QP_BAR_VAL1 = 4, QP_BAR_EV = 5 };
@@ -79,7 +80,7 @@ assemble_cst_pipe_kernel(int c, int n, int nxi, const double* __restrict__ xi_ar
     const int tid = threadIdx.x;
     const unsigned long long total = (unsigned long long)nxi * n * 3ULL;
     if (tid < 2 * QG) sh.slot[tid].nint = 0;
-    if (tid < 2) { sh.nfull[tid] = 0; sh.nerbl[tid] = 0; sh.done[tid] = 0; }
+    if (tid < 2) { sh.nfull[tid][0] = sh.nfull[tid][1] = 0; sh.nerbl[tid][0] = sh.nerbl[tid][1] = 0; sh.done[tid] = 0; }
     __syncthreads();
 
     if (tid < 32 * NBW) {
@@ -152,8 +153,8 @@ assemble_cst_pipe_kernel(int c, int n, int nxi, const double* __restrict__ xi_ar
             __syncwarp();
             const unsigned act = __ballot_sync(0xffffffffu, mine && part == 0 && S.nint != 0);
             if (lane == 0) {
-                sh.nfull[g] = 0;
-                sh.nerbl[g] = 0;
+                sh.nfull[g][0] = sh.nfull[g][1] = 0;
+                sh.nerbl[g][0] = sh.nerbl[g][1] = 0;
                 if (act == 0u) sh.done[g] = 1;
             }
             if (act == 0u) alive &= ~(1 << g);
@@ -170,9 +171,8 @@ assemble_cst_pipe_kernel(int c, int n, int nxi, const double* __restrict__ xi_ar
         if (!((alive >> g) & 1)) continue;
         qp_bar_sync(QP_BAR_REQ0 + g, NRQ);
         if (*(volatile int*)&sh.done[g]) { alive &= ~(1 << g); continue; }
-        unsigned short* live = sh.live[g];
-
-        // ---- N + C: node arguments, support classes, compaction (see assemble_cst_batched.cuh) ----
+        // ---- N + C: node arguments, support classes, compaction (see assemble_cst_batched.cuh); the tasks are
+        // listed per direction so that a warp evaluates one direction (one set of pre-computed values) ----
         for (int e = etid; e < QG * 42; e += NE) {
             const int s = g * QG + e / 42, node = e % 42;
             const QSlot& S = sh.slot[s];
@@ -193,50 +193,60 @@ assemble_cst_pipe_kernel(int c, int n, int nxi, const double* __restrict__ xi_ar
             cls[1] = task_class(xx2, yy2, safe);       // dir 0, half 1
             cls[2] = task_class(yy1, xx1, safe);       // dir 1 (K(y,x)), half 0
             cls[3] = task_class(yy2, xx2, safe);       // dir 1, half 1
-            int nf = 0, ne = 0;
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 if (!HAS_ERBL && cls[k] == 1) cls[k] = 0;
                 if (cls[k] == 0) sh.hv[s][4 * node + k] = 0.0;
-                nf += (cls[k] == 2);
-                ne += (cls[k] == 1);
             }
-            int of = nf ? atomicAdd(&sh.nfull[g], nf) : 0;
-            int oe = ne ? atomicAdd(&sh.nerbl[g], ne) : 0;
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const unsigned short id = (unsigned short)((s - g * QG) * 168 + 4 * node + k);
-                if (cls[k] == 2) live[of++] = id;
-                if (cls[k] == 1) live[QG * 168 - 1 - (oe++)] = id;
+            for (int d = 0; d < 2; d++) {
+                const int nf = (cls[2 * d] == 2) + (cls[2 * d + 1] == 2), ne = (cls[2 * d] == 1) + (cls[2 * d + 1] == 1);
+                int of = nf ? atomicAdd(&sh.nfull[g][d], nf) : 0;
+                int oe = ne ? atomicAdd(&sh.nerbl[g][d], ne) : 0;
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int k = 2 * d + h;
+                    const unsigned short id = (unsigned short)((s - g * QG) * 168 + 4 * node + k);
+                    if (cls[k] == 2) sh.live[g][d][of++] = id;
+                    if (cls[k] == 1) sh.live[g][d][QG * 84 - 1 - (oe++)] = id;
+                }
             }
+        }
+        // one-argument transcendental values of the instances that start in this round (nint == 1)
+        for (int e = etid; e < QG * 2 * PRE_N; e += NE) {
+            const int s = g * QG + e / (2 * PRE_N), v = e % (2 * PRE_N);
+            const QSlot& S = sh.slot[s];
+            if (S.nint == 1) sh.pre[s][v / PRE_N][v % PRE_N] = pre_value(v % PRE_N, (v / PRE_N) ? S.xx2 : S.xx1);
         }
         qp_bar_sync(QP_BAR_EV, NE);
 
-        // ---- E: evaluate the live half kernels ----
-        const int nfull = *(volatile int*)&sh.nfull[g], nerbl = *(volatile int*)&sh.nerbl[g];
-        for (int idx = etid; idx < nfull; idx += NE) {
-            const int e = live[idx];
-            const int sl = e / 168, task = e - 168 * sl, s = g * QG + sl;
-            const QSlot& S = sh.slot[s];
-            const int node = task >> 2, dir = (task >> 1) & 1, half = task & 1;
-            const double yy1 = sh.ny[s][node][0], yy2 = sh.ny[s][node][1];
-            const double U1 = dir ? yy1 : S.xx1, U2 = dir ? yy2 : S.xx2;
-            const double V1 = dir ? S.xx1 : yy1, V2 = dir ? S.xx2 : yy2;
-            double out[NKERN];
-            eval_half<bit(KID), true>(half ? U2 : U1, half ? V2 : V1, half ? U1 : U2, half ? V1 : V2, out);
-            sh.hv[s][task] = out[KID];
-        }
-        if (HAS_ERBL) {
-            for (int idx = etid; idx < nerbl; idx += NE) {
-                const int e = live[QG * 168 - 1 - idx];
+        // ---- E: evaluate the live half kernels.  Four segments (direction x {full, erbl-only}), each padded
+        // to whole warps so that a warp runs one variant ----
+        {
+            const int n0 = *(volatile int*)&sh.nfull[g][0], n1 = *(volatile int*)&sh.nfull[g][1];
+            const int n2 = HAS_ERBL ? *(volatile int*)&sh.nerbl[g][0] : 0, n3 = HAS_ERBL ? *(volatile int*)&sh.nerbl[g][1] : 0;
+            const int p0 = (n0 + 31) & ~31, p1 = p0 + ((n1 + 31) & ~31), p2 = p1 + ((n2 + 31) & ~31), p3 = p2 + ((n3 + 31) & ~31);
+            for (int idx = etid; idx < p3; idx += NE) {
+                const int seg = (idx < p0) ? 0 : ((idx < p1) ? 1 : ((idx < p2) ? 2 : 3));
+                const int j = idx - ((seg == 0) ? 0 : ((seg == 1) ? p0 : ((seg == 2) ? p1 : p2)));
+                const int cnt = (seg == 0) ? n0 : ((seg == 1) ? n1 : ((seg == 2) ? n2 : n3));
+                if (j >= cnt) continue;
+                const int dir = seg & 1;
+                const int e = (seg < 2) ? sh.live[g][dir][j] : sh.live[g][dir][QG * 84 - 1 - j];
                 const int sl = e / 168, task = e - 168 * sl, s = g * QG + sl;
                 const QSlot& S = sh.slot[s];
-                const int node = task >> 2, dir = (task >> 1) & 1, half = task & 1;
+                const int node = task >> 2, half = task & 1;
                 const double yy1 = sh.ny[s][node][0], yy2 = sh.ny[s][node][1];
                 const double U1 = dir ? yy1 : S.xx1, U2 = dir ? yy2 : S.xx2;
                 const double V1 = dir ? S.xx1 : yy1, V2 = dir ? S.xx2 : yy2;
+                const double X = half ? U2 : U1, Y = half ? V2 : V1, Xo = half ? U1 : U2, Yo = half ? V1 : V2;
+                const double* preS = sh.pre[s][half];
+                const double* preO = sh.pre[s][half ^ 1];
                 double out[NKERN];
-                eval_half<bit(KID), false>(half ? U2 : U1, half ? V2 : V1, half ? U1 : U2, half ? V1 : V2, out);
+                if (seg == 0) eval_half<bit(KID), true, 1>(X, Y, Xo, Yo, out, preS, preO);
+                else if (seg == 1) eval_half<bit(KID), true, 2>(X, Y, Xo, Yo, out, preS, preO);
+                else if (seg == 2) eval_half<bit(KID), false, 1>(X, Y, Xo, Yo, out, preS, preO);
+                else eval_half<bit(KID), false, 2>(X, Y, Xo, Yo, out, preS, preO);
                 sh.hv[s][task] = out[KID];
             }
         }

@@ -28,8 +28,9 @@ struct QReplayShared {
     double ny[QBv][42][2];
     double hv[QBv][NKER][168];
     double fv[QBv][NKER][42];
-    unsigned short live[QBv * 168];
-    int nfull, nerbl;
+    double pre[QBv][2][PRE_N];          // per instance and half: one-argument transcendental values (eval_half, FIX)
+    unsigned short live[2][QBv * 84];   // per direction: full tasks from the front, erbl-only from the back
+    int nfull[2], nerbl[2];
     int ev[QBv];                         // instance needs an evaluation in this round
     int have[QBv];                       // fv[slot][0] holds the values of the current request
     int insync[QBv];                     // follower: still on the leader's path
@@ -178,7 +179,7 @@ assemble_cst_replay_kernel(int c, int n, int nxi, const double* __restrict__ xi_
             }
             if (mine && part == 0) sh.ev[myslot] = (S.nint != 0 && !sh.have[myslot]) ? 1 : 0;
         }
-        if (tid == 0) { sh.nfull = 0; sh.nerbl = 0; }
+        if (tid == 0) { sh.nfull[0] = sh.nfull[1] = 0; sh.nerbl[0] = sh.nerbl[1] = 0; }
         __syncthreads();
         const int any = __syncthreads_or(tid < QBv && sh.slot[tid < QBv ? tid : 0].nint != 0);
         if (!any) break;
@@ -206,7 +207,6 @@ assemble_cst_replay_kernel(int c, int n, int nxi, const double* __restrict__ xi_
             cls[1] = task_class(xx2, yy2, safe);
             cls[2] = task_class(yy1, xx1, safe);
             cls[3] = task_class(yy2, xx2, safe);
-            int nf = 0, ne = 0;
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 if (!KS::HAS_ERBL && cls[k] == 1) cls[k] = 0;
@@ -214,46 +214,58 @@ assemble_cst_replay_kernel(int c, int n, int nxi, const double* __restrict__ xi_
 #pragma unroll
                     for (int m = 0; m < NKER; m++) sh.hv[s][m][4 * node + k] = 0.0;
                 }
-                nf += (cls[k] == 2);
-                ne += (cls[k] == 1);
             }
-            int of = nf ? atomicAdd(&sh.nfull, nf) : 0;
-            int oe = ne ? atomicAdd(&sh.nerbl, ne) : 0;
+            // tasks are listed per direction so that a warp evaluates one direction (one set of pre-computed values)
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const unsigned short id = (unsigned short)(s * 168 + 4 * node + k);
-                if (cls[k] == 2) sh.live[of++] = id;
-                if (cls[k] == 1) sh.live[QBv * 168 - 1 - (oe++)] = id;
+            for (int d = 0; d < 2; d++) {
+                const int nf = (cls[2 * d] == 2) + (cls[2 * d + 1] == 2), ne = (cls[2 * d] == 1) + (cls[2 * d + 1] == 1);
+                int of = nf ? atomicAdd(&sh.nfull[d], nf) : 0;
+                int oe = ne ? atomicAdd(&sh.nerbl[d], ne) : 0;
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int k = 2 * d + h;
+                    const unsigned short id = (unsigned short)(s * 168 + 4 * node + k);
+                    if (cls[k] == 2) sh.live[d][of++] = id;
+                    if (cls[k] == 1) sh.live[d][QBv * 84 - 1 - (oe++)] = id;
+                }
             }
+        }
+        // one-argument transcendental values of the instances whose first request is evaluated in this round
+        for (int e = tid; e < QBv * 2 * PRE_N; e += QTv) {
+            const int s = e / (2 * PRE_N), v = e % (2 * PRE_N);
+            const QSlot& S = sh.slot[s];
+            if (sh.ev[s] && (S.nint == 1 || FOLLOW))
+                sh.pre[s][v / PRE_N][v % PRE_N] = pre_value(v % PRE_N, (v / PRE_N) ? S.xx2 : S.xx1);
         }
         __syncthreads();
 
-        // ---------------- E: evaluate the live half kernels (all kernels of the set at once) ----------------
-        const int nfull = sh.nfull, nerbl = sh.nerbl;
-        for (int idx = tid; idx < nfull; idx += QTv) {
-            const int e = sh.live[idx];
-            const int s = e / 168, task = e - 168 * s;
-            const QSlot& S = sh.slot[s];
-            const int node = task >> 2, dir = (task >> 1) & 1, half = task & 1;
-            const double yy1 = sh.ny[s][node][0], yy2 = sh.ny[s][node][1];
-            const double U1 = dir ? yy1 : S.xx1, U2 = dir ? yy2 : S.xx2;
-            const double V1 = dir ? S.xx1 : yy1, V2 = dir ? S.xx2 : yy2;
-            double out[NKERN];
-            eval_half<KS::MASK, true>(half ? U2 : U1, half ? V2 : V1, half ? U1 : U2, half ? V1 : V2, out);
-#pragma unroll
-            for (int m = 0; m < NKER; m++) sh.hv[s][m][task] = out[KS::kid(m)];
-        }
-        if (KS::HAS_ERBL) {
-            for (int idx = tid; idx < nerbl; idx += QTv) {
-                const int e = sh.live[QBv * 168 - 1 - idx];
+        // ---------------- E: evaluate the live half kernels (all kernels of the set at once).  Four segments
+        // (direction x {full, erbl-only}), each padded to whole warps so that a warp runs one variant ----------------
+        {
+            const int n0 = sh.nfull[0], n1 = sh.nfull[1];
+            const int n2 = KS::HAS_ERBL ? sh.nerbl[0] : 0, n3 = KS::HAS_ERBL ? sh.nerbl[1] : 0;
+            const int p0 = (n0 + 31) & ~31, p1 = p0 + ((n1 + 31) & ~31), p2 = p1 + ((n2 + 31) & ~31), p3 = p2 + ((n3 + 31) & ~31);
+            for (int idx = tid; idx < p3; idx += QTv) {
+                const int seg = (idx < p0) ? 0 : ((idx < p1) ? 1 : ((idx < p2) ? 2 : 3));
+                const int j = idx - ((seg == 0) ? 0 : ((seg == 1) ? p0 : ((seg == 2) ? p1 : p2)));
+                const int cnt = (seg == 0) ? n0 : ((seg == 1) ? n1 : ((seg == 2) ? n2 : n3));
+                if (j >= cnt) continue;
+                const int dir = seg & 1;
+                const int e = (seg < 2) ? sh.live[dir][j] : sh.live[dir][QBv * 84 - 1 - j];
                 const int s = e / 168, task = e - 168 * s;
                 const QSlot& S = sh.slot[s];
-                const int node = task >> 2, dir = (task >> 1) & 1, half = task & 1;
+                const int node = task >> 2, half = task & 1;
                 const double yy1 = sh.ny[s][node][0], yy2 = sh.ny[s][node][1];
                 const double U1 = dir ? yy1 : S.xx1, U2 = dir ? yy2 : S.xx2;
                 const double V1 = dir ? S.xx1 : yy1, V2 = dir ? S.xx2 : yy2;
+                const double X = half ? U2 : U1, Y = half ? V2 : V1, Xo = half ? U1 : U2, Yo = half ? V1 : V2;
+                const double* preS = sh.pre[s][half];
+                const double* preO = sh.pre[s][half ^ 1];
                 double out[NKERN];
-                eval_half<KS::MASK, false>(half ? U2 : U1, half ? V2 : V1, half ? U1 : U2, half ? V1 : V2, out);
+                if (seg == 0) eval_half<KS::MASK, true, 1>(X, Y, Xo, Yo, out, preS, preO);
+                else if (seg == 1) eval_half<KS::MASK, true, 2>(X, Y, Xo, Yo, out, preS, preO);
+                else if (seg == 2) eval_half<KS::MASK, false, 1>(X, Y, Xo, Yo, out, preS, preO);
+                else eval_half<KS::MASK, false, 2>(X, Y, Xo, Yo, out, preS, preO);
 #pragma unroll
                 for (int m = 0; m < NKER; m++) sh.hv[s][m][task] = out[KS::kid(m)];
             }

@@ -257,8 +257,25 @@ __device__ inline double combine_halves_rt(int kid, double h1, double h2, double
 // it is implemented for the kernels the QAGS constants need.
 constexpr unsigned MASK_QAGS = bit(K_NSP) | bit(K_NSM) | bit(K_NSN) | bit(K_V1GG) | bit(K_A1GG) | bit(K_V1GGN) | bit(K_A1GGN);
 
-template <unsigned MASK, bool WITH_RHO = true>
-__device__ __forceinline__ void eval_half(double X, double Y, double Xo, double Yo, double* __restrict__ out)
+//
+// FIX: transcendental values that depend on one argument only are the same for every quadrature node of a
+// QAGS instance (its fixed point x is X in K(x,y) and Y in K(y,x)), so the K2 kernels compute them once per
+// instance with the same functions on the same arguments -- bit-identical values -- and pass them in:
+//   FIX = 1: X (and Xo) belong to the fixed point; FIX = 2: Y does.  preS / preO are the tables
+//   { log|U|, log|1-U|, dilog(U), dilog(1-U), dilog(1-(1-U)) } of U = the fixed argument of this half
+//   (X resp. Y) and of the other half (Xo).  FIX = 0: everything is evaluated here.
+enum { PRE_L = 0, PRE_LB = 1, PRE_D = 2, PRE_DB = 3, PRE_DBB = 4, PRE_N = 5 };
+TKB_DEV double pre_value(int which, double U)
+{
+    const double Ub = 1.0 - U;
+    const double arg = (which == PRE_L || which == PRE_D) ? U : ((which == PRE_DBB) ? 1.0 - Ub : Ub);
+    return (which >= PRE_D) ? dilog(arg) : abslog(arg);
+}
+
+template <unsigned MASK, bool WITH_RHO = true, int FIX = 0>
+__device__ __forceinline__ void eval_half(double X, double Y, double Xo, double Yo, double* __restrict__ out,
+                                          const double* __restrict__ preS = nullptr,
+                                          const double* __restrict__ preO = nullptr)
 {
     static_assert(WITH_RHO || (MASK & ~MASK_QAGS) == 0, "erbl-only evaluation exists for the QAGS kernels only");
     constexpr bool LO_ANY = (MASK & 0x7fu) != 0;
@@ -292,12 +309,12 @@ __device__ __forceinline__ void eval_half(double X, double Y, double Xo, double 
     if (N_lr) lr = abslog(r);
     if (N_lomr) lomr = abslog(omr);
     if (N_lyx1) { yx1 = Y / X - 1.0; lyx1 = abslog(yx1); }
-    if (N_lX) lX = abslog(X);
-    if (N_lXb) lXb = abslog(Xb);
-    if (N_lY) lY = abslog(Y);
-    if (N_DX) DX = dilog(X);
-    if (N_DYb) DYb = dilog(Yb);
-    if (N_DXb) DXb = dilog(Xb);
+    if (N_lX) lX = (FIX == 1) ? preS[PRE_L] : abslog(X);
+    if (N_lXb) lXb = (FIX == 1) ? preS[PRE_LB] : abslog(Xb);
+    if (N_lY) lY = (FIX == 2) ? preS[PRE_L] : abslog(Y);
+    if (N_DX) DX = (FIX == 1) ? preS[PRE_D] : dilog(X);
+    if (N_DYb) DYb = (FIX == 2) ? preS[PRE_DB] : dilog(Yb);
+    if (N_DXb) DXb = (FIX == 1) ? preS[PRE_DB] : dilog(Xb);
     const double L2r = sqlog(lr, r);                      // log2(X/Y)
     const double L2X = sqlog(lX, X);                      // log2(X)
     const double LPXbY = prodlog(lXb, Xb, lY, Y);         // logprod(Xbar, Y)
@@ -307,7 +324,7 @@ __device__ __forceinline__ void eval_half(double X, double Y, double Xo, double 
     if (HV && WITH_RHO) {
         Xbb = 1.0 - Xb;
         G = 2.0 * dilog(1.0 - Xb / Y) + sqlog(lY, Y);
-        DXbb = dilog(Xbb);
+        DXbb = (FIX == 1) ? preS[PRE_DBB] : dilog(Xbb);
     }
 
     // ---------------- LO (kernels_lo.f90:48-221) ----------------
@@ -329,7 +346,7 @@ __device__ __forceinline__ void eval_half(double X, double Y, double Xo, double 
             out[K_NSN] = WITH_RHO ? (-0.5 * CF * beta0 * (R5_3 * QQf + X / Y + QQf * lr)) * rho : 0.0;
         }
         if (NS) {
-            const double lXo = abslog(Xo);
+            const double lXo = (FIX == 1) ? preO[PRE_L] : abslog(Xo);
             const double piece4 = -0.5 * X / Yo * (lX + L2X - 2.0 * prodlog(lX, X, lXo, Xo)) * (CF * CF);
             const double p4 = piece4 * erbl;
             if (!WITH_RHO) {
@@ -341,7 +358,8 @@ __device__ __forceinline__ void eval_half(double X, double Y, double Xo, double 
                 // QQ_hbar(Xo, Y): its X is Xo, its Xbar is 1 - Xo
                 const double Xob = 1.0 - Xo;
                 const double Go = 2.0 * dilog(1.0 - Xo / Y) + sqlog(lY, Y);
-                const double QQhbar = hbar_pp(qq_fab(Xo, Y), qq_fab(Xob, Yb), Go, DYb, prodlog(lXo, Xo, lY, Y), dilog(Xob));
+                const double QQhbar = hbar_pp(qq_fab(Xo, Y), qq_fab(Xob, Yb), Go, DYb, prodlog(lXo, Xo, lY, Y),
+                                               (FIX == 1) ? preO[PRE_DB] : dilog(Xob));
                 const double beta0 = -R11_3 * CA;
                 const double piece1 = (CF * CF) * ((R4_3 - 2.0 * ZETA2) * QQf + 3.0 * X / Y
                     - (1.5 * QQf - 0.5 * X / Yo) * lr
