@@ -1123,17 +1123,22 @@ static int launch_replay_one(int c, int n, int nxi, const double* xi_dev, int gr
 #ifndef TKB_QPBPS
 #define TKB_QPBPS 1
 #endif
-#ifndef TKB_QPBW
-#define TKB_QPBW 2
+#ifndef TKB_QPBWG
+#define TKB_QPBWG 1
+#endif
+#ifndef TKB_QPBWG_NFL
+#define TKB_QPBWG_NFL TKB_QPBWG
 #endif
 template <int KID>
 static int launch_pipe_one(int c, int n, int nxi, const double* xi_dev, int grid_type, QLists* lists, int sms,
                            unsigned long long* counter, double* cst_res, int* cst_last, int* cst_ifail, cudaStream_t st)
 {
-    constexpr int QG = TKB_QPG, NT = TKB_QPT, BPS = TKB_QPBPS, NBW = TKB_QPBW;
+    constexpr int QG = TKB_QPG, NT = TKB_QPT, BPS = TKB_QPBPS;
+    // bookkeeping warps per group: the cheap nfl kernels are bookkeeping-bound
+    constexpr int BWG = (KID == K_NSN || KID == K_V1GGN || KID == K_A1GGN) ? TKB_QPBWG_NFL : TKB_QPBWG;
     static_assert(2 * QG * BPS <= RP_SLOTS * 2, "global list area reserved per SM");
     const size_t smem = sizeof(QPipeShared<QG>);
-    auto kern = assemble_cst_pipe_kernel<KID, QG, NT, BPS, NBW>;
+    auto kern = assemble_cst_pipe_kernel<KID, QG, NT, BPS, BWG>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
     const unsigned long long total = (unsigned long long)nxi * n * 3ULL;
@@ -1142,6 +1147,18 @@ static int launch_pipe_one(int c, int n, int nxi, const double* xi_dev, int grid
     if (nb > want) nb = want;
     kern<<<(int)nb, NT, smem, st>>>(c, n, nxi, xi_dev, grid_type, lists, counter, cst_res, cst_last, cst_ifail);
     TKB_LAUNCH_CHECK();
+#ifdef TKB_K2_STATS
+    {
+        cudaStreamSynchronize(st);
+        unsigned long long h[16];
+        cudaMemcpyFromSymbol(h, g_k2stats, sizeof h);
+        fprintf(stderr, "K2 pipe stats KID %d: bookkeeper per round: wait-values %.0f, bookkeeping %.0f, wait-REQ %.0f cyc (%llu rounds) | evaluators per round: wait-requests %.0f, work %.0f cyc (%llu rounds)\n",
+                KID, h[3] ? (double)h[0] / h[3] : 0., h[3] ? (double)h[1] / h[3] : 0., h[3] ? (double)h[2] / h[3] : 0., h[3],
+                h[6] ? (double)h[4] / h[6] : 0., h[6] ? (double)h[5] / h[6] : 0., h[6]);
+        unsigned long long z[16] = { 0 };
+        cudaMemcpyToSymbol(g_k2stats, z, sizeof z);
+    }
+#endif
     return 0;
 }
 

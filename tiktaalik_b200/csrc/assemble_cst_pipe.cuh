@@ -28,7 +28,9 @@ struct QPipeShared {
     double fv[2 * QG][42];
     double pre[2 * QG][2][PRE_N];       // per instance and half: one-argument transcendental values (eval_half, FIX)
     unsigned short live[2][2][QG * 84]; // per group and direction: full tasks from the front, erbl-only from the back
-    int nfull[2][2], nerbl[2][2], done[2];
+    int nfull[2][2], nerbl[2][2];
+    int next[2];                        // E phase: next 32-task chunk of the group
+    int act[2][8];                      // per group and bookkeeping warp: it still has a running instance
 };
 
 enum { QP_BAR_REQ0 = 1, QP_BAR_REQ1 = 2, QP_BAR_VAL0 = 3, QP_BAR_VAL1 = 4, QP_BAR_EV = 5 };
@@ -64,35 +66,40 @@ __device__ __forceinline__ void qp_bar_arrive(int id, int count)
     }
 }
 
-template <int KID, int QG, int NT, int BPS, int NBW>
+template <int KID, int QG, int NT, int BPS, int BWG>
 __global__ void __launch_bounds__(NT, BPS)
 assemble_cst_pipe_kernel(int c, int n, int nxi, const double* __restrict__ xi_arr, int grid_type,
                          QLists* __restrict__ lists, unsigned long long* __restrict__ counter,
                          double* __restrict__ cst_res, int* __restrict__ cst_last, int* __restrict__ cst_ifail)
 {
-    static_assert(2 * QG <= 32, "one lane pair per instance of a group in the bookkeeping warp");
-    static_assert(NBW == 1 || NBW == 2, "one bookkeeping warp for both groups, or one per group");
-    constexpr int NE = NT - 32 * NBW;                 // evaluator threads
-    constexpr int NRQ = NE + 32;                      // participants of a hand-over barrier: one bookkeeping warp + evaluators
+        static_assert(BWG >= 1 && QG % BWG == 0 && 2 * (QG / BWG) <= 32, "BWG bookkeeping warps per group, one lane pair per instance");
+    constexpr int NBK = 2 * BWG * 32;                 // bookkeeping threads (both groups)
+    constexpr int NE = NT - NBK;                      // evaluator threads
+    constexpr int NRQ = NE + 32 * BWG;                // participants of a hand-over barrier: a group's bookkeepers + evaluators
     constexpr bool HAS_ERBL = (KID != K_NSN);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     QPipeShared<QG>& sh = *reinterpret_cast<QPipeShared<QG>*>(smem_raw);
     const int tid = threadIdx.x;
     const unsigned long long total = (unsigned long long)nxi * n * 3ULL;
     if (tid < 2 * QG) sh.slot[tid].nint = 0;
-    if (tid < 2) { sh.nfull[tid][0] = sh.nfull[tid][1] = 0; sh.nerbl[tid][0] = sh.nerbl[tid][1] = 0; sh.done[tid] = 0; }
+    if (tid < 2) { sh.nfull[tid][0] = sh.nfull[tid][1] = 0; sh.nerbl[tid][0] = sh.nerbl[tid][1] = 0; sh.next[tid] = 0; }
     __syncthreads();
 
-    if (tid < 32 * NBW) {
-        // ======================= bookkeeper =======================
+    if (tid < NBK) {
+        // ======================= bookkeepers: warp b of group g owns the instances b, b + BWG, ... =======================
         const int lane = tid & 31, part = lane & 1;
-        const bool mine = (lane >> 1) < QG;
+        const int g = (tid >> 5) / BWG, bw = (tid >> 5) % BWG;
+        const bool mine = (lane >> 1) < QG / BWG;
         bool exhausted = false;
-        int alive = (NBW == 2) ? (1 << (tid >> 5)) : 3, g = (NBW == 2) ? (tid >> 5) : 0;
-        for (int round = 0; alive != 0; round++, g ^= (NBW == 2 ? 0 : 1)) {
-            if (!((alive >> g) & 1)) continue;
-            if (round >= (NBW == 2 ? 1 : 2)) qp_bar_sync(QP_BAR_VAL0 + g, NRQ);      // the first round(s) only pull instances
-            const int myslot = g * QG + (mine ? (lane >> 1) : 0);
+        for (int round = 0;; round++) {
+#ifdef TKB_K2_STATS
+            long long tb0_ = clock64();
+#endif
+            if (round >= 1) qp_bar_sync(QP_BAR_VAL0 + g, NRQ);      // the first round only pulls instances
+#ifdef TKB_K2_STATS
+            long long tb1_ = clock64();
+#endif
+            const int myslot = g * QG + (mine ? (bw + BWG * (lane >> 1)) : 0);
             QSlot& S = sh.slot[myslot];
             QLists* myL = lists + (size_t)blockIdx.x * (2 * QG) + myslot;
             const int nint0 = mine ? S.nint : 0;
@@ -153,24 +160,54 @@ assemble_cst_pipe_kernel(int c, int n, int nxi, const double* __restrict__ xi_ar
             __syncwarp();
             const unsigned act = __ballot_sync(0xffffffffu, mine && part == 0 && S.nint != 0);
             if (lane == 0) {
-                sh.nfull[g][0] = sh.nfull[g][1] = 0;
-                sh.nerbl[g][0] = sh.nerbl[g][1] = 0;
-                if (act == 0u) sh.done[g] = 1;
+                if (bw == 0) {
+                    sh.nfull[g][0] = sh.nfull[g][1] = 0;
+                    sh.nerbl[g][0] = sh.nerbl[g][1] = 0;
+                    sh.next[g] = 0;
+                }
+                sh.act[g][bw] = (act != 0u) ? 1 : 0;
             }
-            if (act == 0u) alive &= ~(1 << g);
             __syncwarp();
-            qp_bar_arrive(QP_BAR_REQ0 + g, NRQ);
+            // the group's bookkeepers and the evaluators meet here; all of them then read the same act[] flags
+            // (rewritten only after the next VAL barrier, which needs every reader's arrival)
+#ifdef TKB_K2_STATS
+            long long tb2_ = clock64();
+#endif
+            qp_bar_sync(QP_BAR_REQ0 + g, NRQ);
+#ifdef TKB_K2_STATS
+            if (lane == 0 && bw == 0) {
+                atomicAdd(&g_k2stats[0], (unsigned long long)(tb1_ - tb0_));          // bookkeeper waits for values
+                atomicAdd(&g_k2stats[1], (unsigned long long)(tb2_ - tb1_));          // bookkeeping
+                atomicAdd(&g_k2stats[2], (unsigned long long)(clock64() - tb2_));     // waits for the evaluators at REQ
+                atomicAdd(&g_k2stats[3], 1ULL);
+            }
+#endif
+            int any = 0;
+#pragma unroll
+            for (int b = 0; b < BWG; b++) any |= *(volatile int*)&sh.act[g][b];
+            if (!any) break;
         }
         return;
     }
 
     // ======================= evaluators =======================
-    const int etid = tid - 32 * NBW;
+    const int etid = tid - NBK;
     int alive = 3;
     for (int g = 0; alive != 0; g ^= 1) {
         if (!((alive >> g) & 1)) continue;
+#ifdef TKB_K2_STATS
+        long long te0_ = clock64();
+#endif
         qp_bar_sync(QP_BAR_REQ0 + g, NRQ);
-        if (*(volatile int*)&sh.done[g]) { alive &= ~(1 << g); continue; }
+#ifdef TKB_K2_STATS
+        long long te1_ = clock64();
+#endif
+        {
+            int any = 0;
+#pragma unroll
+            for (int b = 0; b < BWG; b++) any |= *(volatile int*)&sh.act[g][b];
+            if (!any) { alive &= ~(1 << g); continue; }
+        }
         // ---- N + C: node arguments, support classes, compaction (see assemble_cst_batched.cuh); the tasks are
         // listed per direction so that a warp evaluates one direction (one set of pre-computed values) ----
         for (int e = etid; e < QG * 42; e += NE) {
@@ -221,17 +258,25 @@ assemble_cst_pipe_kernel(int c, int n, int nxi, const double* __restrict__ xi_ar
         qp_bar_sync(QP_BAR_EV, NE);
 
         // ---- E: evaluate the live half kernels.  Four segments (direction x {full, erbl-only}), each padded
-        // to whole warps so that a warp runs one variant ----
+        // to whole warps so that a warp runs one variant; the warps draw 32-task chunks from a counter, most
+        // expensive segment first (K(y,x) needs more transcendental values than K(x,y)), so that the cheap
+        // chunks fill the end of the phase ----
         {
-            const int n0 = *(volatile int*)&sh.nfull[g][0], n1 = *(volatile int*)&sh.nfull[g][1];
-            const int n2 = HAS_ERBL ? *(volatile int*)&sh.nerbl[g][0] : 0, n3 = HAS_ERBL ? *(volatile int*)&sh.nerbl[g][1] : 0;
+            const int n0 = *(volatile int*)&sh.nfull[g][1], n1 = *(volatile int*)&sh.nfull[g][0];
+            const int n2 = HAS_ERBL ? *(volatile int*)&sh.nerbl[g][1] : 0, n3 = HAS_ERBL ? *(volatile int*)&sh.nerbl[g][0] : 0;
             const int p0 = (n0 + 31) & ~31, p1 = p0 + ((n1 + 31) & ~31), p2 = p1 + ((n2 + 31) & ~31), p3 = p2 + ((n3 + 31) & ~31);
-            for (int idx = etid; idx < p3; idx += NE) {
+            const int elane = etid & 31;
+            for (;;) {
+                int chunk = 0;
+                if (elane == 0) chunk = atomicAdd(&sh.next[g], 1);
+                chunk = __shfl_sync(0xffffffffu, chunk, 0);
+                const int idx = chunk * 32 + elane;
+                if (chunk * 32 >= p3) break;
                 const int seg = (idx < p0) ? 0 : ((idx < p1) ? 1 : ((idx < p2) ? 2 : 3));
                 const int j = idx - ((seg == 0) ? 0 : ((seg == 1) ? p0 : ((seg == 2) ? p1 : p2)));
                 const int cnt = (seg == 0) ? n0 : ((seg == 1) ? n1 : ((seg == 2) ? n2 : n3));
                 if (j >= cnt) continue;
-                const int dir = seg & 1;
+                const int dir = (seg & 1) ^ 1;
                 const int e = (seg < 2) ? sh.live[g][dir][j] : sh.live[g][dir][QG * 84 - 1 - j];
                 const int sl = e / 168, task = e - 168 * sl, s = g * QG + sl;
                 const QSlot& S = sh.slot[s];
@@ -243,9 +288,9 @@ assemble_cst_pipe_kernel(int c, int n, int nxi, const double* __restrict__ xi_ar
                 const double* preS = sh.pre[s][half];
                 const double* preO = sh.pre[s][half ^ 1];
                 double out[NKERN];
-                if (seg == 0) eval_half<bit(KID), true, 1>(X, Y, Xo, Yo, out, preS, preO);
-                else if (seg == 1) eval_half<bit(KID), true, 2>(X, Y, Xo, Yo, out, preS, preO);
-                else if (seg == 2) eval_half<bit(KID), false, 1>(X, Y, Xo, Yo, out, preS, preO);
+                if (seg == 1) eval_half<bit(KID), true, 1>(X, Y, Xo, Yo, out, preS, preO);
+                else if (seg == 0) eval_half<bit(KID), true, 2>(X, Y, Xo, Yo, out, preS, preO);
+                else if (seg == 3) eval_half<bit(KID), false, 1>(X, Y, Xo, Yo, out, preS, preO);
                 else eval_half<bit(KID), false, 2>(X, Y, Xo, Yo, out, preS, preO);
                 sh.hv[s][task] = out[KID];
             }
@@ -264,6 +309,13 @@ assemble_cst_pipe_kernel(int c, int n, int nxi, const double* __restrict__ xi_ar
             }
         }
         qp_bar_arrive(QP_BAR_VAL0 + g, NRQ);
+#ifdef TKB_K2_STATS
+        if (etid == 0) {
+            atomicAdd(&g_k2stats[4], (unsigned long long)(te1_ - te0_));              // evaluators wait for requests
+            atomicAdd(&g_k2stats[5], (unsigned long long)(clock64() - te1_));         // N+C, E, K
+            atomicAdd(&g_k2stats[6], 1ULL);
+        }
+#endif
     }
 }
 
