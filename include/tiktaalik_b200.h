@@ -86,6 +86,13 @@ int tkb_apply(int m, int nxi, int nq2, int64_t S, const double* M_dev, const dou
 int tkb_gk(int which, int nx, int nxi, int nt, const double* x_dev, const double* xi_dev, const double* t_dev,
            double* out_dev, void* stream);
 
+/* -Ofast ambiguity of the reference build: gfortran may have compiled the float32 divisions by the
+ * pixel count -- real(2*i-1)/real(n_pixels), convolution.f90:45,67,92, and real(2*iStart-1)/real(Nx_cache),
+ * pixelation.f90:85 -- as multiplications by a rounded reciprocal, which moves 1/6 of the nodes by one float32
+ * ulp and kernel entries by up to 2e-4.  0 = IEEE division (canonical, the default), 1 = reciprocal multiply;
+ * applies to the next tkb_make_kernels.  The oracle has the same switches (oracle/tko_grid.c). */
+int tkb_set_variant(int eta_recip_f32, int x0_recip_f32);
+
 /* releases every device buffer of the implicit context */
 int tkb_free(void);
 

@@ -91,6 +91,7 @@ double tko_push_jacob(double eta, double xi, int nx, int grid_type);
 void   tko_initialize_lagrange_weights(int nx, int norder);
 double tko_interpixel(int n_pixels, int i, double x, double xi, int grid_type);
 void   tko_pixelspace(int nx, double xi, int grid_type, double *x);   /* f90wrap/matrices.f90:21-30 */
+void tko_set_variant(int eta_recip_f32, int x0_recip_f32);             /* -Ofast float32-division variants, SURVEY 8c */
 double tko_grid_node(int i, int nx, double xi, int grid_type);       /* convolution.f90:45-46 */
 
 /* test hooks for the primitives of tko_fp.h */

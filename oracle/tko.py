@@ -51,7 +51,7 @@ def lib():
             "tko_push_jacob": (d, [d, d, i, i]),
             "tko_initialize_lagrange_weights": (None, [i, i]),
             "tko_interpixel": (d, [i, i, d, d, i]),
-            "tko_pixelspace": (None, [i, d, i, _dp]), "tko_grid_node": (d, [i, i, d, i]),
+            "tko_pixelspace": (None, [i, d, i, _dp]), "tko_grid_node": (d, [i, i, d, i]), "tko_set_variant": (None, [i, i]),
             "tko_qk21": (None, [F1, C.c_void_p, d, d, _dp, _dp, _dp, _dp]),
             "tko_qags": (None, [F1, C.c_void_p, d, d, d, d, _dp, _dp, _ip, _ip, _ip]),
             "tko_get_alpha_qcd": (d, [d]), "tko_get_neff": (i, [d]),
@@ -127,6 +127,11 @@ def pixelspace(nx, xi=0.5, grid_type=1):
     x = np.empty(nx)
     lib().tko_pixelspace(nx, float(xi), grid_type, _ptr(x))
     return x
+
+
+def set_variant(eta_recip_f32=False, x0_recip_f32=False):
+    """-Ofast float32-division variants of the node formula / stencil origin; (False, False) is canonical."""
+    lib().tko_set_variant(int(bool(eta_recip_f32)), int(bool(x0_recip_f32)))
 
 
 def grid_nodes(nx, xi, grid_type):

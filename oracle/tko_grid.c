@@ -104,6 +104,20 @@ static double lagrange_basis(double x, double x0, int i)
     return w_table[i] * prod;
 }
 
+/* -Ofast ambiguity: the reference is built with -Ofast, which may turn the two float32
+ * divisions by the loop-invariant pixel count into multiplications by a rounded reciprocal.  A 1-ulp float32
+ * change of a node moves kernel entries by up to 2e-4, so the choice is exposed: strict IEEE division (0, the
+ * canonical variant) or reciprocal multiply (1), separately for the node formula (convolution.f90:45,67,92)
+ * and the stencil origin (pixelation.f90:85).  tkb_set_variant is the GPU side's switch. */
+static int eta_recip_f32 = 0, x0_recip_f32 = 0;
+void tko_set_variant(int eta_recip, int x0_recip) { eta_recip_f32 = eta_recip != 0; x0_recip_f32 = x0_recip != 0; }
+static float quot_f32(float a, float b, int recip)
+{
+    if (!recip) return a / b;
+    volatile float r = 1.0f / b;              /* rounded reciprocal, kept out of any re-association */
+    return a * r;
+}
+
 /* pixelation.f90:70-87; x0 is evaluated entirely in float32 */
 static double interpolate_lagrange_pixel(int ix, double x)
 {
@@ -113,7 +127,7 @@ static double interpolate_lagrange_pixel(int ix, double x)
     if (iStart > Nx_cache + 1 - N_order_cache) iStart = Nx_cache + 1 - N_order_cache;
     int iEnd = iStart + N_order_cache - 1;
     if (ix < iStart || ix > iEnd) return 0.0;
-    float x0f = -1.0f + (float)(2 * iStart - 1) / (float)Nx_cache;
+    float x0f = -1.0f + quot_f32((float)(2 * iStart - 1), (float)Nx_cache, x0_recip_f32);
     return lagrange_basis(x, (double)x0f, ix - iStart + 1);
 }
 
@@ -127,7 +141,7 @@ double tko_interpixel(int n_pixels, int i, double x, double xi, int grid_type)
 /* convolution.f90:45-46: eta = real(2*i-1)/real(n_pixels) - 1. (all float32), then push_forward */
 double tko_grid_node(int i, int nx, double xi, int grid_type)
 {
-    float etaf = (float)(2 * i - 1) / (float)nx - 1.0f;
+    float etaf = quot_f32((float)(2 * i - 1), (float)nx, eta_recip_f32) - 1.0f;
     return tko_push_forward((double)etaf, xi, nx, grid_type);
 }
 

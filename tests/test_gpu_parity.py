@@ -177,6 +177,32 @@ def test_kernel_matrices_match_oracle(tk, tko, nx, xis, grid_type):
             assert np.array_equal(got, ref, equal_nan=True), "%s nfl=%d not bit-identical" % (name, nfl)
 
 
+@pytest.mark.parametrize("variant", [(1, 0), (0, 1), (1, 1)])
+def test_ofast_variants_bit_identical(tk, tko, variant):
+    """the two float32-division variants of an -Ofast reference build; GPU and oracle take the
+    same switches and stay bit-identical in each (the canonical (0, 0) variant is every other test)."""
+    nx, xis, grid_type = 24, np.array([0.07, 0.4]), 2
+    f90 = tk.f90wrap.matrices.dummy
+    try:
+        tko.set_variant(0, 0)
+        tko.initialize_kernels(nx, xis, grid_type, mode=1)
+        canon = tko.raw_kernel(tko.RAW_NAMES[0], 3).copy()
+        f90.set_variant(*variant)
+        tko.set_variant(*variant)
+        tk.matrices.initialize_kernels(nx, xis, grid_type=grid_type)
+        tko.initialize_kernels(nx, xis, grid_type, mode=1)
+        for which, name in enumerate(tko.RAW_NAMES):
+            got = _raw_gpu(tk, which, 4)
+            ref = tko.raw_kernel(name, 4)
+            assert np.array_equal(got, ref, equal_nan=True), "%s variant %s not bit-identical" % (name, variant)
+        # the switch does something: entries move at the 1e-4 level, not the 1e-15 level
+        moved = np.abs(tko.raw_kernel(tko.RAW_NAMES[0], 3) - canon).max() / np.abs(canon).max()
+        assert 1e-9 < moved < 1e-2, moved
+    finally:
+        f90.set_variant(0, 0)
+        tko.set_variant(0, 0)
+
+
 @pytest.mark.parametrize("nlo", [False, True])
 def test_evolution_matrices_match_oracle(tk, tko, nlo):
     nx, xis, gt = 16, np.array([0.1, 0.4]), 1

@@ -175,3 +175,19 @@ def test_block_identities_and_lo_sum_rules(tko):
     tko.initialize_evolution_matrices(np.array([4.0, 10.0]), nlo=True)
     assert np.array_equal(tko.matrix_ANS(1), tko.matrix_VNS(-1))
     assert not np.array_equal(tko.matrix_VNS(1), tko.matrix_VNS(-1))
+
+
+def test_ofast_variant_switches_move_a_sixth_of_the_nodes(tko):
+    """reciprocal-multiply instead of float32 division changes ~1/6 of the nodes by one float32 ulp."""
+    try:
+        tko.set_variant(0, 0)
+        x0 = tko.grid_nodes(160, 0.1, 1)
+        tko.set_variant(1, 0)
+        x1 = tko.grid_nodes(160, 0.1, 1)
+        changed = int((x0 != x1).sum())
+        assert 10 <= changed <= 60, changed
+        assert np.abs(x1 - x0).max() <= 2.0 ** -23
+        tko.set_variant(0, 1)
+        assert np.array_equal(tko.grid_nodes(160, 0.1, 1), x0)          # x0 switch does not touch the nodes
+    finally:
+        tko.set_variant(0, 0)

@@ -41,6 +41,7 @@ SIGNATURES = {
     "tkb_eval_scalar": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "tkb_stage_ms": (C.c_int, [_dp]),
     "tkb_launch_count": (C.c_longlong, []),
+    "tkb_set_variant": (C.c_int, [C.c_int, C.c_int]),
     "tkb_fp64_peak": (C.c_int, [_dp]),
 }
 

@@ -78,6 +78,7 @@ assemble_fixed_kernel(int n, int nxi, const double* __restrict__ xi_arr, int gri
     __shared__ double s_aa[8], s_hl[6], s_w[6], s_bx[6];
     __shared__ int s_iSx;
     __shared__ int s_allfinite;
+    __shared__ double s_pre[2][PRE_N];        // one-argument logs/dilogs of the row's fixed point (eval_half, FIX = 1)
 
     const int i = blockIdx.x + 1;             // 1-based row
     const int ixi = blockIdx.y;
@@ -108,6 +109,11 @@ assemble_fixed_kernel(int n, int nxi, const double* __restrict__ xi_arr, int gri
         for (int m = 0; m < 6; m++) s_bx[m] = bx[m];
         s_allfinite = 1;
     }
+    if (tid >= 32 && tid < 32 + 2 * PRE_N) {     // a second warp, while thread 0 sets up the breakpoints
+        const int v = tid - 32;
+        const double X1 = 0.5 * (1.0 + x / xi), X2 = 0.5 * (1.0 - x / xi);
+        s_pre[v / PRE_N][v % PRE_N] = pre_value(v % PRE_N, (v / PRE_N) ? X2 : X1);
+    }
     __syncthreads();
 
     // ---- phase 1: one thread per (node, half) ----
@@ -136,8 +142,8 @@ assemble_fixed_kernel(int n, int nxi, const double* __restrict__ xi_arr, int gri
             }
             const double X1 = 0.5 * (1.0 + x / xi), X2 = 0.5 * (1.0 - x / xi);
             const double Y1 = 0.5 * (1.0 + y / xi), Y2 = 0.5 * (1.0 - y / xi);
-            if (half == 0) eval_half<MASK_ALL>(X1, Y1, X2, Y2, hv);
-            else eval_half<MASK_ALL>(X2, Y2, X1, Y1, hv);
+            if (half == 0) eval_half<MASK_ALL, true, 1>(X1, Y1, X2, Y2, hv, s_pre[0], s_pre[1]);
+            else eval_half<MASK_ALL, true, 1>(X2, Y2, X1, Y1, hv, s_pre[1], s_pre[0]);
         } else {
 #pragma unroll
             for (int f = 0; f < NKERN; f++) hv[f] = 0.0;
@@ -1001,6 +1007,14 @@ __global__ void eval_scalar_kernel(int which, int npts, const double* __restrict
         ++g_launches;                                                        \
         if (e_ != cudaSuccess) return set_error(cudaGetErrorString(e_));     \
     } while (0)
+
+int set_grid_variant(int eta_recip_f32, int x0_recip_f32)
+{
+    const int v[2] = { eta_recip_f32 != 0, x0_recip_f32 != 0 };
+    const cudaError_t e = cudaMemcpyToSymbol(c_variant, v, sizeof v);
+    if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
+    return 0;
+}
 
 int launch_assemble_fixed(int n, int nxi, const double* xi_dev, int grid_type, double* P, double* diag, cudaStream_t st)
 {

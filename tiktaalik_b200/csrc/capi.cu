@@ -550,6 +550,12 @@ int tkb_stage_ms(double ms[3])
 
 long long tkb_launch_count(void) { return g_launches; }
 
+int tkb_set_variant(int eta_recip_f32, int x0_recip_f32)
+{
+    // takes effect at the next tkb_make_kernels; kernels assembled before are not touched
+    return set_grid_variant(eta_recip_f32, x0_recip_f32);
+}
+
 int tkb_fp64_peak(double* tflops)
 {
     int dev = 0, sms = 148;

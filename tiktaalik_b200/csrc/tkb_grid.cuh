@@ -10,6 +10,15 @@
 
 namespace tkb {
 
+// -Ofast ambiguity of the reference build: the float32 divisions by the pixel count may have been
+// compiled as multiplications by a rounded reciprocal.  [0]: node formula (convolution.f90:45,67,92), [1]: stencil
+// origin (pixelation.f90:85); 0 = IEEE division (canonical), 1 = reciprocal multiply.  Set by tkb_set_variant.
+static __constant__ int c_variant[2] = { 0, 0 };
+TKB_DEV float quot_f32(float a, float b, int recip)
+{
+    return recip ? __fmul_rn(a, __frcp_rn(b)) : __fdiv_rn(a, b);
+}
+
 TKB_DEV double push_forward(double eta, double xi, int grid_type)
 {
     if (grid_type == 2) {
@@ -43,7 +52,7 @@ TKB_DEV double push_jacob(double eta, double xi, int grid_type)
 // x_i = push_forward( real(2*i-1)/real(n) - 1. ), the subtraction in float32 (convolution.f90:45)
 TKB_DEV double grid_node(int i /*1-based*/, int n, double xi, int grid_type)
 {
-    const float etaf = __fsub_rn(__fdiv_rn((float)(2 * i - 1), (float)n), 1.0f);
+    const float etaf = __fsub_rn(quot_f32((float)(2 * i - 1), (float)n, c_variant[0]), 1.0f);
     return push_forward((double)etaf, xi, grid_type);
 }
 
@@ -69,7 +78,7 @@ TKB_DEV int basis_row(double eta, int n, const double* __restrict__ w, double* _
     int iStart = iloc - 2;
     if (iStart < 1) iStart = 1;
     if (iStart > n - 5) iStart = n - 5;
-    const float x0f = __fadd_rn(-1.0f, __fdiv_rn((float)(2 * iStart - 1), (float)n));
+    const float x0f = __fadd_rn(-1.0f, quot_f32((float)(2 * iStart - 1), (float)n, c_variant[1]));
     const double x0 = (double)x0f;
     const double dx = (double)__fdiv_rn(2.0f, (float)n);
     double lf[6];

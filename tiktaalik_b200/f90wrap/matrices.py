@@ -51,6 +51,12 @@ class _Dummy:
                                                      int(grid_type), int(clamp_first), int(clamp_last),
                                                      _lib.stream_ptr()))
 
+    @staticmethod
+    def set_variant(eta_recip_f32=False, x0_recip_f32=False):
+        """-Ofast float32-division variant of the node formula / stencil origin (not an f2py name)."""
+        _lib.require_cuda()
+        _lib.check(_lib.lib().tkb_set_variant(int(bool(eta_recip_f32)), int(bool(x0_recip_f32))))
+
     # ---- make_matrices_wrap (:43-53) ----
     @staticmethod
     def make_matrices_wrap(q2_array, l_nlo, nq2=None):
