@@ -93,6 +93,19 @@ int tkb_gk(int which, int nx, int nxi, int nt, const double* x_dev, const double
  * applies to the next tkb_make_kernels.  The oracle has the same switches (oracle/tko_grid.c). */
 int tkb_set_variant(int eta_recip_f32, int x0_recip_f32);
 
+/* ---- multi-GPU: one process per GPU, xi-sharded.  Every loop of the reference is independent
+ * across xi (matevo.f90:291,325,359,381,426,452,514,550,584), so ranks assemble and step their own block with
+ * tkb_make_kernels_shard / tkb_make_matrices and exchange nothing; the one optional collective is the final
+ * all-gather of the matrices along xi.  NCCL is bound at run time (dlopen), not at link time.
+ * tkb_shard_unique_id: rank 0 creates the 128-byte NCCL id, the host program distributes it (MPI, torch.distributed
+ * store, a file); tkb_shard_init: every rank joins (binds the communicator to its current CUDA device);
+ * tkb_allgather_matrices: dev_out[sum nxi_per_rank][nq2][m][m] receives every rank's [xi][Q2][i][j] slab in rank
+ * order (type / nstype as tkb_evomatrix; nxi_per_rank[rank] must equal this rank's xi count), enqueued on `stream`. */
+int tkb_shard_unique_id(char id_out[128]);
+int tkb_shard_init(const char id_in[128], int rank, int world);
+int tkb_allgather_matrices(int type, int nstype, const int* nxi_per_rank, double* dev_out, void* stream);
+int tkb_shard_finalize(void);
+
 /* releases every device buffer of the implicit context */
 int tkb_free(void);
 

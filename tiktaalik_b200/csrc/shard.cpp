@@ -1,0 +1,132 @@
+// shard.cpp -- the one exchange step of the xi-sharded path: an all-gather of the evolution
+// matrices along xi over NCCL / NVLink.  Assembly, stepping and application need no collective: every loop of
+// the reference is independent across xi (matevo.f90:291,325,359,381,426,452,514,550,584; evolution.py:507-509).
+//
+// The library stores M as [xi][Q2][i][j], so a rank's contribution is one contiguous slab and the gathered
+// array is the concatenation of the slabs in rank order.  Block sizes may differ between ranks, so the gather is
+// one NCCL group of `world` broadcasts (root r writes slab r), in place for the caller's own slab.
+//
+// NCCL is bound at run time (dlopen of libnccl.so.2 -- inside a PyTorch process that is the copy torch has
+// already loaded) so that the library has no link-time dependency on it and single-GPU use never touches it.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/tiktaalik_b200.h"
+#include "tkb_internal.h"
+
+namespace {
+
+struct UniqueId { char internal[128]; };                    // ncclUniqueId (NCCL_UNIQUE_ID_BYTES = 128)
+typedef void* Comm;                                         // ncclComm_t
+enum { kNcclFloat64 = 8 };                                  // ncclDataType_t: ncclFloat64 / ncclDouble
+
+struct Nccl {
+    void* handle = nullptr;
+    int (*GetUniqueId)(UniqueId*) = nullptr;
+    int (*CommInitRank)(Comm*, int, UniqueId, int) = nullptr;
+    int (*CommDestroy)(Comm) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    int (*Broadcast)(const void*, void*, size_t, int, int, Comm, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    Comm comm = nullptr;
+    int rank = 0, world = 1;
+} N;
+
+int nccl_fail(const char* what, int rc)
+{
+    char buf[256];
+    snprintf(buf, sizeof buf, "%s: %s", what, N.GetErrorString ? N.GetErrorString(rc) : "NCCL error");
+    return tkb::set_error(buf);
+}
+
+int load_nccl()
+{
+    if (N.handle) return 0;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return tkb::set_error("tkb_shard: libnccl.so.2 not found (multi-GPU gather needs NCCL)");
+#define TKB_SYM(field, name)                                                                  \
+    *(void**)(&N.field) = dlsym(h, name);                                                     \
+    if (!N.field) { dlclose(h); return tkb::set_error("tkb_shard: NCCL symbol " name " missing"); }
+    TKB_SYM(GetUniqueId, "ncclGetUniqueId")
+    TKB_SYM(CommInitRank, "ncclCommInitRank")
+    TKB_SYM(CommDestroy, "ncclCommDestroy")
+    TKB_SYM(GroupStart, "ncclGroupStart")
+    TKB_SYM(GroupEnd, "ncclGroupEnd")
+    TKB_SYM(Broadcast, "ncclBroadcast")
+    TKB_SYM(GetErrorString, "ncclGetErrorString")
+#undef TKB_SYM
+    N.handle = h;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int tkb_shard_unique_id(char id_out[128])
+{
+    if (!id_out) return tkb::set_error("tkb_shard_unique_id: null pointer");
+    if (load_nccl()) return 1;
+    UniqueId id;
+    const int rc = N.GetUniqueId(&id);
+    if (rc != 0) return nccl_fail("ncclGetUniqueId", rc);
+    memcpy(id_out, id.internal, 128);
+    return 0;
+}
+
+int tkb_shard_init(const char id_in[128], int rank, int world)
+{
+    if (!id_in || world < 1 || rank < 0 || rank >= world) return tkb::set_error("tkb_shard_init: bad arguments");
+    if (load_nccl()) return 1;
+    if (N.comm) { N.CommDestroy(N.comm); N.comm = nullptr; }
+    UniqueId id;
+    memcpy(id.internal, id_in, 128);
+    const int rc = N.CommInitRank(&N.comm, world, id, rank);       // binds to the current CUDA device
+    if (rc != 0) { N.comm = nullptr; return nccl_fail("ncclCommInitRank", rc); }
+    N.rank = rank;
+    N.world = world;
+    return 0;
+}
+
+int tkb_shard_finalize(void)
+{
+    if (N.comm && N.CommDestroy) N.CommDestroy(N.comm);
+    N.comm = nullptr;
+    N.rank = 0;
+    N.world = 1;
+    return 0;
+}
+
+int tkb_allgather_matrices(int type, int nstype, const int* nxi_per_rank, double* dev_out, void* stream)
+{
+    if (!N.comm) return tkb::set_error("tkb_allgather_matrices: call tkb_shard_init first");
+    if (!nxi_per_rank || !dev_out) return tkb::set_error("tkb_allgather_matrices: null pointer");
+    const double* local = nullptr;
+    int64_t shape[4], strides[4];
+    if (tkb_evomatrix(type, nstype, &local, shape, strides)) return 1;
+    const int64_t m = shape[0], nxi = shape[2], nq2 = shape[3];
+    if (nxi_per_rank[N.rank] != nxi) return tkb::set_error("tkb_allgather_matrices: nxi_per_rank[rank] differs from the assembled xi count");
+    const size_t per_xi = (size_t)nq2 * (size_t)m * (size_t)m;
+    int rc = N.GroupStart();
+    if (rc != 0) return nccl_fail("ncclGroupStart", rc);
+    size_t off = 0;
+    for (int r = 0; r < N.world; r++) {
+        if (nxi_per_rank[r] < 0) { N.GroupEnd(); return tkb::set_error("tkb_allgather_matrices: negative block size"); }
+        const size_t count = (size_t)nxi_per_rank[r] * per_xi;
+        if (count) {
+            const void* send = (r == N.rank) ? (const void*)local : (const void*)(dev_out + off);
+            rc = N.Broadcast(send, dev_out + off, count, kNcclFloat64, r, N.comm, (cudaStream_t)stream);
+            if (rc != 0) { N.GroupEnd(); return nccl_fail("ncclBroadcast", rc); }
+        }
+        off += count;
+    }
+    rc = N.GroupEnd();
+    if (rc != 0) return nccl_fail("ncclGroupEnd", rc);
+    return 0;
+}
+
+}  // extern "C"

@@ -78,3 +78,41 @@ def gather_matrix(M_local, counts=None, group=None):
         dist.all_gather_into_tensor(allp, padded, group=group)
         out = torch.cat([allp[r * cmax:r * cmax + c] for r, c in enumerate(counts)], dim=0)
     return out.permute(2, 3, 0, 1)
+
+
+# --------------------------------------------------------------------------------------------
+# the same gather through the library's own C ABI (tkb_shard_init / tkb_allgather_matrices): what a
+# non-Python host would call.  torch.distributed is only used to hand the NCCL id to the other ranks.
+
+_MATRIX_TYPES = {"matrix_VNS": 0, "matrix_VSG": 1, "matrix_ANS": 2, "matrix_ASG": 3}
+
+
+def init_capi(group=None):
+    """Create the library's NCCL communicator over the ranks of `group` (rank 0 makes the id)."""
+    import ctypes as C
+    import torch.distributed as dist
+    from . import _lib
+    _lib.require_cuda()
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    buf = C.create_string_buffer(128)
+    if rank == 0:
+        _lib.check(_lib.lib().tkb_shard_unique_id(buf))
+    box = [buf.raw if rank == 0 else None]
+    dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    _lib.check(_lib.lib().tkb_shard_init(box[0], rank, world))
+
+
+def gather_matrix_capi(name, counts, ns_type=1):
+    """All-gather one matrix family along xi with tkb_allgather_matrices.  name: 'matrix_VNS' | 'matrix_VSG' |
+    'matrix_ANS' | 'matrix_ASG'; counts: xi block sizes of all ranks.  Returns (m, m, nxi_total, nQ2)."""
+    import ctypes as C
+    from . import _lib
+    L = _lib.lib()
+    n, nq = L.tkb_get_nx(), L.tkb_get_nq2()
+    m = n * (2 if name.endswith("SG") else 1)
+    total = int(sum(counts))
+    out = torch.empty((total, nq, m, m), dtype=torch.float64, device=_lib.require_cuda())
+    cnt = (C.c_int * len(counts))(*[int(c) for c in counts])
+    _lib.check(L.tkb_allgather_matrices(_MATRIX_TYPES[name], int(ns_type), cnt, C.c_void_p(out.data_ptr()),
+                                        _lib.stream_ptr()))
+    return out.permute(2, 3, 0, 1)

@@ -29,6 +29,17 @@ for n, ref in full.items():
     got = tk.shard.gather_matrix(getattr(tk.matrices, n)())
     same = tuple(got.shape) == tuple(ref.shape) and torch.equal(got, ref)
     ok = ok and same
+# the same gather through the C ABI (tkb_shard_init / tkb_allgather_matrices)
+counts, _ = tk.shard.xi_partition(xi.shape[0], world)
+tk.shard.init_capi()
+for n, ref in full.items():
+    got = tk.shard.gather_matrix_capi(n, counts)
+    torch.cuda.synchronize()
+    same = tuple(got.shape) == tuple(ref.shape) and torch.equal(got, ref)
+    if not same:
+        print("rank %d: C-ABI gather of %s differs" % (rank, n))
+    ok = ok and same
+tk._lib.lib().tkb_shard_finalize()
 flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
