@@ -312,7 +312,7 @@ def main():
                     "d2h_bytes_per_step": int(d2h_bytes)},
             "gpu_launches": int(launches),
             "application": application,
-            "roofline": {"bound": "fp64", "kernel": "K2, the QAGS constants: assemble_cst_pipe_kernel<KID> x 5 + assemble_cst_replay_kernel (KV1_NSp leader, KV1_NSm follower); duration = the assembly span, which also contains the overlapped fixed-quadrature kernel K1",
+            "roofline": {"bound": "fp64", "kernel": "K2, the QAGS constants: assemble_cst_pipe_kernel<KID> x 7 launches; duration = the assembly span, which also contains the overlapped fixed-quadrature kernel K1",
                          "achieved": k2_tflops, "peak": peak.value, "unit": "TFLOP/s",
                          "frac": k2_tflops / peak.value if peak.value else None, "traffic": fpe.get("traffic_bytes"),
                          "peak_source": "DFMA microbenchmark measured in this run (tkb_fp64_peak); MEASURED_PEAKS.json "

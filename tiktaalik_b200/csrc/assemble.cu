@@ -1194,25 +1194,35 @@ int launch_assemble_cst_replay(int n, int nxi, const double* xi_dev, int grid_ty
     const size_t region = (size_t)RP_SLOTS * sms * 2;
     const int rec_ns = 4 + 42 * 2, rec_gg = 4 + 42 * 3;
 #define RP_ARGS(c) c, n, nxi, xi_dev, grid_type, Lp + region * (c), sms, counters + (c), cst_res, cst_last, cst_ifail
-    // Sharing pays only where the follower's evaluation saving exceeds its (unchanged) bookkeeping cost and
-    // the leader's extra work: measured on C3, KV1_NSm behind KV1_NSp (-19 ms / +4 ms).  The gluon family and
-    // the cheap nfl kernels are bookkeeping-bound as followers, so they run unshared.
+    // Sharing (TKB_K2_MODE=share|replay) paid in the lock-step form only where the follower's evaluation saving
+    // exceeded its (unchanged) bookkeeping cost and the leader's extra work: KV1_NSm behind KV1_NSp (-19 ms / +4 ms
+    // on C3); the gluon family and the cheap nfl kernels are bookkeeping-bound as followers.
     const int rec_pair = 4 + 42;
-    // unshared constants: role-split pipeline (assemble_cst_pipe.cuh) unless TKB_K2_MODE=replay asks for the
-    // lock-step form
+    // role-split pipeline (assemble_cst_pipe.cuh) unless TKB_K2_MODE=replay asks for the lock-step form
     const char* mode_ = getenv("TKB_K2_MODE");
     const bool pipe = !(mode_ && mode_[0] == 'r');
 #define RP_PLAIN(c, KID, strm)                                                                                        \
     if (pipe ? launch_pipe_one<KID>(RP_ARGS(c), strm)                                                                  \
              : launch_replay_one<KID, -1, -1, -1, false, 16, 384>(RP_ARGS(c), nullptr, nullptr, 0, 0, 0, strm)) return 1;
+    // KV1_NSp / KV1_NSm as leader / follower (assemble_cst_replay.cuh) only on request: with the pipeline and the
+    // per-instance tables two unshared launches are faster (C3: K2 150 ms against 160 ms)
+    const bool share_ns = (mode_ && (mode_[0] == 's' || mode_[0] == 'r'));
     RP_PLAIN(3, K_V1GG, side[0])
-    if (launch_replay_one<K_NSP, K_NSM, -1, -1, false, 14, 352>(RP_ARGS(0), log_ns, nlog_ns, L, rec_pair, 0, side[1])) return 1;
-    e = cudaEventRecord(leader_done[0], side[1]);
-    if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
+    if (share_ns) {
+        if (launch_replay_one<K_NSP, K_NSM, -1, -1, false, 14, 352>(RP_ARGS(0), log_ns, nlog_ns, L, rec_pair, 0, side[1])) return 1;
+        e = cudaEventRecord(leader_done[0], side[1]);
+        if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
+    } else {
+        RP_PLAIN(0, K_NSP, side[1])
+    }
     RP_PLAIN(4, K_A1GG, side[2])
-    e = cudaStreamWaitEvent(side[5], leader_done[0], 0);
-    if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
-    if (launch_replay_one<K_NSM, -1, -1, -1, true, 16, 384>(RP_ARGS(1), log_ns, nlog_ns, L, rec_pair, 0, side[5])) return 1;
+    if (share_ns) {
+        e = cudaStreamWaitEvent(side[5], leader_done[0], 0);
+        if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
+        if (launch_replay_one<K_NSM, -1, -1, -1, true, 16, 384>(RP_ARGS(1), log_ns, nlog_ns, L, rec_pair, 0, side[5])) return 1;
+    } else {
+        RP_PLAIN(1, K_NSM, side[5])
+    }
     RP_PLAIN(5, K_V1GGN, side[3])
     RP_PLAIN(6, K_A1GGN, side[4])
     RP_PLAIN(2, K_NSN, side[6])

@@ -172,8 +172,9 @@ static int make_kernels_impl(int nx, int nxi, const double* xi_host, int grid_ty
     int nblocks = sms * 8;        // more than fit at once: the spare blocks start as others drain
     if (const char* env = getenv("TKB_K2_BLOCKS_PER_SM")) { const int v = atoi(env); if (v > 0) nblocks = sms * v; }   // tuning knob
     if ((long long)nblocks > want) nblocks = (int)want;
-    // K2 form: leader/follower replay (default), batched without sharing (TKB_K2_MODE=batched), or one
-    // instance per warp (TKB_K2_MODE=warp); the last two are kept for comparison
+    // K2 form: role-split pipeline, one launch per constant (default).  Kept for comparison behind TKB_K2_MODE:
+    // share (KV1_NSp / KV1_NSm as leader / follower with an evaluation log), replay (lock-step blocks for all,
+    // with that sharing), batched (lock-step, no sharing), warp (one instance per warp)
     const char* mode = getenv("TKB_K2_MODE");
     const bool warpmode = (mode && mode[0] == 'w');
     const bool replay = !(mode && (mode[0] == 'w' || mode[0] == 'b'));
@@ -195,8 +196,14 @@ static int make_kernels_impl(int nx, int nxi, const double* xi_host, int grid_ty
             CUDA_OK(cudaMalloc(&g.scratch, need));
             g.scratch_bytes = need;
         }
-        const size_t dn = qags_replay_log_doubles(0, ninst, L), dg = qags_replay_log_doubles(1, ninst, L);
-        const size_t lneed = (dn + dg) * sizeof(double) + 2 * ninst * sizeof(int);
+        const bool sharing = (mode && (mode[0] == 's' || mode[0] == 'r'));
+        const size_t dn = sharing ? qags_replay_log_doubles(0, ninst, L) : 0, dg = 0;
+        const size_t lneed = sharing ? dn * sizeof(double) + 2 * ninst * sizeof(int) : 0;
+        if (!sharing && g.qlog) {            // the evaluation log of an earlier sharing run is not needed any more
+            cudaFree(g.qlog);
+            g.qlog = nullptr;
+            g.qlog_bytes = 0;
+        }
         if (g.qlog_bytes < lneed) {
             if (g.qlog) cudaFree(g.qlog);
             g.qlog = nullptr;
@@ -204,7 +211,7 @@ static int make_kernels_impl(int nx, int nxi, const double* xi_host, int grid_ty
             CUDA_OK(cudaMalloc(&g.qlog, lneed));
             g.qlog_bytes = lneed;
         }
-        int* nl = (int*)(g.qlog + dn + dg);
+        int* nl = sharing ? (int*)(g.qlog + dn + dg) : nullptr;
         rc = launch_assemble_cst_replay(nx, nxi, g.d_xi, grid_type, (char*)g.scratch + 64, sms,
                                         (unsigned long long*)g.scratch, g.cst_res, g.cst_last, g.cst_ifail,
                                         g.qlog, g.qlog + dn, nl, nl + ninst, L, st, g.side, g.fork, g.join, g.leader_done);
