@@ -90,11 +90,13 @@ static inline double tko_log(double x)
     double s = f / (2.0 + f);
     double z = s * s;
     double w = z * z;
-    double t1 = w * (TKO_LG2 + w * (TKO_LG4 + w * TKO_LG6));
-    double t2 = z * (TKO_LG1 + w * (TKO_LG3 + w * (TKO_LG5 + w * TKO_LG7)));
+    /* fdlibm e_log.c with the Horner steps and the final sums fused; the library's log_core fuses the same ones */
+    double t1 = w * fma(w, fma(w, TKO_LG6, TKO_LG4), TKO_LG2);
+    double t2 = z * fma(w, fma(w, fma(w, TKO_LG7, TKO_LG5), TKO_LG3), TKO_LG1);
     double R = t2 + t1;
     double dk = (double)k;
-    return s * (hfsq + R) + dk * TKO_LN2_LO - hfsq + f + dk * TKO_LN2_HI;
+    double u = fma(s, hfsq + R, dk * TKO_LN2_LO);
+    return fma(dk, TKO_LN2_HI, f - (hfsq - u));
 }
 
 /* log(x) = hi + lo with ~2^-60 relative accuracy, x positive finite non-zero */

@@ -117,8 +117,8 @@ static __device__ __noinline__ double dilog(double z)
     case 4: w = omz; la = z; lb = omz; break;
     default: w = z; la = 1.0; lb = 1.0; break;
     }
-    const double l1 = log_(la);
-    const double l2 = log_(lb);
+    const double l1 = log_or_zero(la);
+    const double l2 = log_or_zero(lb);
     double D = dilog_half(w);
     if (rg != 5 && rg != 6) {                 // the inner call of the reference sees the special points too
         if (w == 0.0) D = 0.0;
