@@ -86,33 +86,39 @@ assemble_fixed_kernel(int n, int nxi, const double* __restrict__ xi_arr, int gri
     const double xi = xi_arr[ixi];
     const double x = grid_node(i, n, xi, grid_type);
 
-    if (tid == 0) {
-        // integration.f90:27-35: breakpoints in eta space, inner pairs sorted
-        double aa[8];
-        aa[1] = pull_back(-1.0, xi, grid_type);
-        aa[2] = pull_back(-fabs(x), xi, grid_type);
-        aa[3] = pull_back(-fabs(xi), xi, grid_type);
-        aa[4] = pull_back(0.0, xi, grid_type);
-        aa[5] = pull_back(fabs(xi), xi, grid_type);
-        aa[6] = pull_back(fabs(x), xi, grid_type);
-        aa[7] = pull_back(1.0, xi, grid_type);
-        if (aa[3] < aa[2]) { const double z = aa[2]; aa[2] = aa[3]; aa[3] = z; }
-        if (aa[6] < aa[5]) { const double z = aa[5]; aa[5] = aa[6]; aa[6] = z; }
-        for (int r = 1; r <= 7; r++) s_aa[r] = aa[r];
-        for (int r = 0; r < 6; r++) s_hl[r] = 5.0e-01 * (aa[r + 2] - aa[r + 1]);
+    // set-up, spread over a few threads of different warps (every piece is a chain of dependent log / pow / divisions):
+    // integration.f90:27-35 breakpoints in eta space; Lagrange weights; eta of x_i; the row's one-argument logs/dilogs
+    if (tid < 7) {
+        const double ax = fabs(x), axi = fabs(xi);
+        const double arg = (tid == 0) ? -1.0 : (tid == 1) ? -ax : (tid == 2) ? -axi : (tid == 3) ? 0.0
+                         : (tid == 4) ? axi : (tid == 5) ? ax : 1.0;
+        s_aa[tid + 1] = pull_back(arg, xi, grid_type);
+    } else if (tid == 32) {
         double w[6];
         lagrange_weights(n, w);
         for (int m = 0; m < 6; m++) s_w[m] = w[m];
-        // basis row at x_i itself (interpixel(j, x): pull_back then Lagrange, convolution.f90:77,93)
-        double bx[6];
-        s_iSx = basis_row(pull_back(x, xi, grid_type), n, w, bx);
-        for (int m = 0; m < 6; m++) s_bx[m] = bx[m];
+    } else if (tid == 64) {
+        s_aa[0] = pull_back(x, xi, grid_type);                 // eta of x_i, for the basis row below
         s_allfinite = 1;
-    }
-    if (tid >= 32 && tid < 32 + 2 * PRE_N) {     // a second warp, while thread 0 sets up the breakpoints
-        const int v = tid - 32;
+    } else if (tid >= 96 && tid < 96 + 2 * PRE_N) {
+        const int v = tid - 96;
         const double X1 = 0.5 * (1.0 + x / xi), X2 = 0.5 * (1.0 - x / xi);
         s_pre[v / PRE_N][v % PRE_N] = pre_value(v % PRE_N, (v / PRE_N) ? X2 : X1);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double aa[8];
+        for (int r = 1; r <= 7; r++) aa[r] = s_aa[r];
+        if (aa[3] < aa[2]) { const double z = aa[2]; aa[2] = aa[3]; aa[3] = z; }      // inner pairs sorted
+        if (aa[6] < aa[5]) { const double z = aa[5]; aa[5] = aa[6]; aa[6] = z; }
+        for (int r = 1; r <= 7; r++) s_aa[r] = aa[r];
+        for (int r = 0; r < 6; r++) s_hl[r] = 5.0e-01 * (aa[r + 2] - aa[r + 1]);
+    } else if (tid == 32) {
+        // basis row at x_i itself (interpixel(j, x): pull_back then Lagrange, convolution.f90:77,93)
+        double w[6], bx[6];
+        for (int m = 0; m < 6; m++) w[m] = s_w[m];
+        s_iSx = basis_row(s_aa[0], n, w, bx);
+        for (int m = 0; m < 6; m++) s_bx[m] = bx[m];
     }
     __syncthreads();
 
@@ -167,9 +173,52 @@ assemble_fixed_kernel(int n, int nxi, const double* __restrict__ xi_arr, int gri
     const int iSx = s_iSx;
     const size_t rowbase = ((size_t)ixi * n + (size_t)(i - 1)) * n;
     const size_t fstride = (size_t)nxi * n * n;
+    // The six columns whose basis function is non-zero at x_i carry the subtraction term f_j(x_i) of the plus
+    // kernels at every node (66 accumulation steps instead of the ~4 of an ordinary column).  They are split
+    // by kernel, one thread per (column, kernel), so that no thread walks all nodes for all 22 kernels.
+    if (!dense && tid < 6 * NKERN) {
+        const int jh = tid / NKERN, f = tid - NKERN * jh;
+        const int j = iSx + jh;
+        const double fx = s_bx[jh];
+        if (fx != 0.0) {
+            const bool plus = is_plus(f);
+            double integral = 0.0;
+            for (int r = 0; r < 6; r++) {
+                double resk = 0.0;
+                for (int s = 0; s <= 10; s++) {
+                    const int t = (s == 0) ? 11 : ((s <= 5) ? 2 * s : 2 * (s - 5) - 1);
+                    const int k1 = 21 * r + ((s == 0) ? 0 : 2 * t - 1);
+                    const int k2 = k1 + 1;
+                    const int m1 = j - s_iS[k1];
+                    const bool in1 = (m1 >= 0 && m1 < 6);
+                    bool in2 = false;
+                    int m2 = 0;
+                    if (s != 0) { m2 = j - s_iS[k2]; in2 = (m2 >= 0 && m2 < 6); }
+                    if (!(plus || in1 || in2)) continue;
+                    const double fy1 = in1 ? s_b[k1][m1] : 0.0;
+                    const double J1 = s_J[k1];
+                    const double w = c_wgk[t];
+                    if (s == 0) {
+                        const double fc = plus ? (s_K[f][k1] * (fy1 - fx)) * J1 : (s_K[f][k1] * fy1) * J1;
+                        resk = w * fc;
+                    } else {
+                        const double fy2 = in2 ? s_b[k2][m2] : 0.0;
+                        const double J2 = s_J[k2];
+                        const double v1 = plus ? (s_K[f][k1] * (fy1 - fx)) * J1 : (s_K[f][k1] * fy1) * J1;
+                        const double v2 = plus ? (s_K[f][k2] * (fy2 - fx)) * J2 : (s_K[f][k2] * fy2) * J2;
+                        const double fsum = v1 + v2;
+                        resk = resk + w * fsum;
+                    }
+                }
+                integral = integral + resk * s_hl[r];
+            }
+            P[(size_t)f * fstride + rowbase + (size_t)(j - 1)] = integral;
+        }
+    }
     for (int j = tid + 1; j <= n; j += K1_THREADS) {
         const int mx = j - iSx;
         const double fx = (mx >= 0 && mx < 6) ? s_bx[mx] : 0.0;
+        if (!dense && fx != 0.0) continue;                     // done above, one thread per kernel
         double integral[NKERN];
 #pragma unroll
         for (int f = 0; f < NKERN; f++) integral[f] = 0.0;
