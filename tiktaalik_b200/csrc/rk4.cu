@@ -144,6 +144,10 @@ constexpr int DM_WT = 40;            // warp tile
 constexpr int DM_NT = DM_WT / 8;     // MMA tiles per warp-tile side
 constexpr int DM_PAD = 4;            // smem row stride 84 doubles = 8 banks mod 32: the 4 k-rows of a fragment load hit disjoint banks
 
+// NJ = MMA tiles per warp along N: the block tile is 80 rows x 16 NJ columns.  NJ = 5 is the square 80 x 80 tile;
+// NJ = 1..4 serve the application to 9..64 samples, where one narrow tile covers all columns, so that M is
+// streamed from HBM exactly once and no MMA work is spent on padding columns.
+template <int NJ>
 __global__ void __launch_bounds__(128)
 gemm_dmma_kernel(int M, int N, int K, double alpha,
                  const double* __restrict__ A, int lda, int64_t strideA,
@@ -151,26 +155,28 @@ gemm_dmma_kernel(int M, int N, int K, double alpha,
                  const double* __restrict__ D, int ldd, int64_t strideD,
                  double* __restrict__ C, int ldc, int64_t strideC)
 {
+    constexpr int BN = 16 * NJ;                           // block tile columns
     __shared__ double As[2][GEMM_BK][DM_BT + DM_PAD];     // As[stage][k][m]
-    __shared__ double Bs[2][GEMM_BK][DM_BT + DM_PAD];     // Bs[stage][k][n]
+    __shared__ double Bs[2][GEMM_BK][BN + DM_PAD];        // Bs[stage][k][n]
     const int b = blockIdx.z;
     A += (int64_t)b * strideA;
     B += (int64_t)(b / bdivB) * strideB;
     C += (int64_t)b * strideC;
     if (D) D += (int64_t)b * strideD;
-    const int row0 = blockIdx.y * DM_BT, col0 = blockIdx.x * DM_BT;
+    const int row0 = blockIdx.y * DM_BT, col0 = blockIdx.x * BN;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int wr = (warp >> 1) * DM_WT, wc = (warp & 1) * DM_WT;        // warp tile origin inside the block tile
+    const int wr = (warp >> 1) * DM_WT, wc = (warp & 1) * (8 * NJ);        // warp tile origin inside the block tile
     const int fr = lane >> 2, fk = lane & 3;                              // fragment coordinates
 
-    double acc[DM_NT][DM_NT][2];
+    double acc[DM_NT][NJ][2];
 #pragma unroll
     for (int i = 0; i < DM_NT; i++)
 #pragma unroll
-        for (int j = 0; j < DM_NT; j++) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+        for (int j = 0; j < NJ; j++) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
 
-    constexpr int NLD = (DM_BT * GEMM_BK) / 128;          // 10 loads per thread for each operand tile
-    double ra[NLD], rb[NLD];
+    constexpr int NLD = (DM_BT * GEMM_BK) / 128;          // 10 loads per thread for the A tile
+    constexpr int NLB = (BN * GEMM_BK) / 128;             // 2 NJ loads per thread for the B tile
+    double ra[NLD], rb[NLB];
     auto load_tile = [&](int k0) {
 #pragma unroll
         for (int u = 0; u < NLD; u++) {
@@ -180,9 +186,9 @@ gemm_dmma_kernel(int M, int N, int K, double alpha,
             ra[u] = (gr < M && gk < K) ? __ldg(A + (int64_t)gr * lda + gk) : 0.0;
         }
 #pragma unroll
-        for (int u = 0; u < NLD; u++) {
+        for (int u = 0; u < NLB; u++) {
             const int e = tid + 128 * u;
-            const int kk = e / DM_BT, c = e - kk * DM_BT;  // B: 16 k x 80 cols, cols fastest
+            const int kk = e / BN, c = e - kk * BN;        // B: 16 k x BN cols, cols fastest
             const int gk = k0 + kk, gc = col0 + c;
             rb[u] = (gk < K && gc < N) ? __ldg(B + (int64_t)gk * ldb + gc) : 0.0;
         }
@@ -194,10 +200,10 @@ gemm_dmma_kernel(int M, int N, int K, double alpha,
             As[st][e & 15][e >> 4] = ra[u];
         }
 #pragma unroll
-        for (int u = 0; u < NLD; u++) {
+        for (int u = 0; u < NLB; u++) {
             const int e = tid + 128 * u;
-            const int kk = e / DM_BT;
-            Bs[st][kk][e - kk * DM_BT] = rb[u];
+            const int kk = e / BN;
+            Bs[st][kk][e - kk * BN] = rb[u];
         }
     };
 
@@ -210,15 +216,15 @@ gemm_dmma_kernel(int M, int N, int K, double alpha,
         if (more) load_tile(k0 + GEMM_BK);
 #pragma unroll
         for (int k4 = 0; k4 < GEMM_BK; k4 += 4) {
-            double af[DM_NT], bf[DM_NT];
+            double af[DM_NT], bf[NJ];
 #pragma unroll
             for (int i = 0; i < DM_NT; i++) af[i] = As[st][k4 + fk][wr + 8 * i + fr];
 #pragma unroll
-            for (int j = 0; j < DM_NT; j++) bf[j] = Bs[st][k4 + fk][wc + 8 * j + fr];
+            for (int j = 0; j < NJ; j++) bf[j] = Bs[st][k4 + fk][wc + 8 * j + fr];
 #pragma unroll
             for (int i = 0; i < DM_NT; i++)
 #pragma unroll
-                for (int j = 0; j < DM_NT; j++) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+                for (int j = 0; j < NJ; j++) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
         }
         if (more) store_tile(st ^ 1);
         __syncthreads();
@@ -229,7 +235,7 @@ gemm_dmma_kernel(int M, int N, int K, double alpha,
         const int gr = row0 + wr + 8 * i + fr;
         if (gr >= M) continue;
 #pragma unroll
-        for (int j = 0; j < DM_NT; j++) {
+        for (int j = 0; j < NJ; j++) {
             const int gc = col0 + wc + 8 * j + 2 * fk;
 #pragma unroll
             for (int h = 0; h < 2; h++) {
@@ -260,11 +266,31 @@ int launch_gemm(int M, int N, int K, double alpha,
         const double* Bb = B + (int64_t)(b0 / bdivB) * strideB;
         const double* Db = D ? D + (int64_t)b0 * strideD : nullptr;
         double* Cb = C + (int64_t)b0 * strideC;
-        if (N >= 40 && !g_gemm_no_dmma) {
-            dim3 grid((N + DM_BT - 1) / DM_BT, (M + DM_BT - 1) / DM_BT, nb);
-            gemm_dmma_kernel<<<grid, 128, 0, st>>>(M, N, K, alpha, Ab, lda, strideA, Bb, ldb, strideB, bdivB, Db, ldd,
-                                                   strideD, Cb, ldc, strideC);
-        } else if (t5) {
+#define TKB_DMMA(NJ)                                                                                                  \
+    {                                                                                                                 \
+        dim3 grid((N + 16 * NJ - 1) / (16 * NJ), (M + DM_BT - 1) / DM_BT, nb);                                        \
+        gemm_dmma_kernel<NJ><<<grid, 128, 0, st>>>(M, N, K, alpha, Ab, lda, strideA, Bb, ldb, strideB, bdivB, Db, ldd, \
+                                                   strideD, Cb, ldc, strideC);                                        \
+    }
+        // tile width 16 NJ: the one that wastes the least time on padding columns; measured throughput of a full
+        // tile on B200 (TFLOP/s at N = 16 NJ, m = 320): 14.3, 22.7, 25.6, 27.7, 24.2
+        int best = 0;
+        if (N > 8 && M >= 40 && !g_gemm_no_dmma) {
+            const double eff[5] = { 14.3, 22.7, 25.6, 27.7, 24.2 };
+            double cost = 0.0;
+            for (int nj = 1; nj <= 5; nj++) {
+                const int w = 16 * nj;
+                const double c = (double)(((N + w - 1) / w) * w) / eff[nj - 1];
+                if (best == 0 || c < cost) { best = nj; cost = c; }
+            }
+        }
+        if (best == 5) TKB_DMMA(5)
+        else if (best == 4) TKB_DMMA(4)
+        else if (best == 3) TKB_DMMA(3)
+        else if (best == 2) TKB_DMMA(2)
+        else if (best == 1) TKB_DMMA(1)
+#undef TKB_DMMA
+        else if (t5) {
             dim3 grid((N + 79) / 80, (M + 79) / 80, nb);
             gemm_kernel<5><<<grid, 256, 0, st>>>(M, N, K, alpha, Ab, lda, strideA, Bb, ldb, strideB, bdivB, Db, ldd,
                                                  strideD, Cb, ldc, strideC);
