@@ -248,7 +248,7 @@ def test_kernel_getters_match_oracle(tk, tko):
 # --------------------------------------------------------------------------------------------
 # application
 
-@pytest.mark.parametrize("S", [1, 3, 8, 9, 16, 23, 40, 64, 65, 200])
+@pytest.mark.parametrize("S", [1, 3, 4, 5, 8, 9, 16, 23, 40, 64, 65, 200])
 def test_apply_matches_einsum(tk, S):
     rng = np.random.default_rng(5)
     m, nxi, nq = 24, 3, 4

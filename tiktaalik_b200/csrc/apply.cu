@@ -7,9 +7,12 @@
 //     M   [xi][Q2][i][j]   row-major m x m tiles (what make_matrices produces)
 //     g   [j][xi][s]       the caller's (m, nxi, S) C-contiguous array, consumed in place
 //     out [xi][Q2][i][s]   returned to Python as a permuted view of shape (m, nxi, S, nQ2)
-// Two regimes: S <= 8 is HBM-bound on reading M (0.25..1.9 flop/B) and uses a
-// warp-per-row kernel with 16-byte coalesced loads; larger S is FP64-bound and uses the
-// batched GEMM of rk4.cu with the right-hand side shared by the nQ2 matrices of one xi.
+// Two regimes: small S is HBM-bound on reading M (0.25..1.9 flop/B) and uses a
+// warp-per-row kernel with 16-byte coalesced loads (S <= 4 by default; the kernel exists up to 8,
+// TKB_APPLY_SMALL_MAX); larger S uses the batched FP64 tensor-core GEMM of rk4.cu with a tile as
+// narrow as the sample count and the right-hand side shared by the nQ2 matrices of one xi
+// (HBM-bound up to S ~ 24, FP64-bound beyond).
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include "tkb_internal.h"
 
@@ -83,7 +86,8 @@ int launch_apply(int m, int nxi, int nq2, int64_t S, const double* M, const doub
 {
     if (S <= 0) return 0;
     const int nb = nxi * nq2;
-    if (S <= GEMV_MAXS && (m % 2) == 0 && (size_t)m * S * sizeof(double) <= 48 * 1024) {
+    static const int small_max = [] { const char* e = getenv("TKB_APPLY_SMALL_MAX"); const int v = e ? atoi(e) : 4;   /* measured: from S = 5 the narrow-tile DMMA GEMM is faster */ return v < 0 ? 0 : (v > GEMV_MAXS ? GEMV_MAXS : v); }();
+    if (S <= small_max && (m % 2) == 0 && (size_t)m * S * sizeof(double) <= 48 * 1024) {
         switch ((int)S) {
         case 1: return launch_small<1>(m, nb, nq2, M, g, ldg, out, st);
         case 2: return launch_small<2>(m, nb, nq2, M, g, ldg, out, st);

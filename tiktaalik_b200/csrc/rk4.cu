@@ -275,7 +275,7 @@ int launch_gemm(int M, int N, int K, double alpha,
         // tile width 16 NJ: the one that wastes the least time on padding columns; measured throughput of a full
         // tile on B200 (TFLOP/s at N = 16 NJ, m = 320): 14.3, 22.7, 25.6, 27.7, 24.2
         int best = 0;
-        if (N > 8 && M >= 40 && !g_gemm_no_dmma) {
+        if (N > 4 && M >= 40 && !g_gemm_no_dmma) {
             const double eff[5] = { 14.3, 22.7, 25.6, 27.7, 24.2 };
             double cost = 0.0;
             for (int nj = 1; nj <= 5; nj++) {
