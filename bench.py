@@ -121,13 +121,15 @@ def run_reference(args, rank, world):
         return
     threads = os.cpu_count() or 1
     xi_all = np.geomspace(XI_MIN, XI_MAX, NXI_PER_RANK * world)
-    sample = np.array([xi_all[len(xi_all) // 2]])                 # one mid-range xi per step (~5-15 s of CPU)
+    # four xi spanning the range per step (QAGS cost varies with xi): ~7 s of CPU per step on 16 threads
+    sample = xi_all[[len(xi_all) // 8, (3 * len(xi_all)) // 8, (5 * len(xi_all)) // 8, (7 * len(xi_all)) // 8]]
     for _ in range(args.warmup):
         cpu_reference_step(sample, threads)
     times = [cpu_reference_step(sample, threads) for _ in range(args.steps)]
     t = float(np.sum(times))
     value = args.steps * sample.shape[0] / t
-    sample_txt = "1 of %d xi (xi=%.3e) per step, full nx=160 NLO assembly + RK4" % (len(xi_all), sample[0])
+    sample_txt = "4 of %d xi (%s) per step, full nx=160 NLO assembly + RK4" % (
+        len(xi_all), ", ".join("%.2e" % v for v in sample))
     line = {
         "impl": "reference", "metric": "evolution-matrix sets/sec (xi pts/s) at nx=160 NLO", "value": value,
         "unit": "xi pts/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -318,16 +320,19 @@ def main():
                          "peak_source": "DFMA microbenchmark measured in this run (tkb_fp64_peak); MEASURED_PEAKS.json "
                                         "has HBM and bf16 only",
                          "share_of_step": stage[1] / (ms / args.steps),
+                         "k2_integrand_evaluations_per_s": float(neval_c.sum()) / (stage[1] * 1e-3) if stage[1] > 0 else None,
+                         "k1_kernel_evaluations_per_step": 2898.0 * NX * xi.shape[0],
                          "flops_per_eval_source": fpe.get("source", "estimate (no ncu capture yet)")},
         }
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             xi_all = np.geomspace(XI_MIN, XI_MAX, NXI_PER_RANK * world)
-            sample = xi_all[[len(xi_all) // 4, (3 * len(xi_all)) // 4]]
+            sample = xi_all[np.linspace(len(xi_all) // 16, len(xi_all) - 1 - len(xi_all) // 16, 8).astype(int)]
             t = cpu_reference_step(sample, threads)
             line["cpu_baseline"] = {"value": sample.shape[0] / t, "unit": "xi pts/s", "cores": threads, "kind": "port",
-                                    "sample": "2 of %d xi (xi=%.2e, %.2e), full nx=160 NLO assembly + RK4, "
-                                              "reference-shaped unfactored loop nest, %.1f s" % (len(xi_all), sample[0], sample[1], t)}
+                                    "sample": "8 of %d xi (strided over the range, %.2e .. %.2e), full nx=160 NLO "
+                                              "assembly + RK4, reference-shaped unfactored loop nest, %.1f s"
+                                              % (len(xi_all), sample[0], sample[-1], t)}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
