@@ -71,7 +71,13 @@ __global__ void __launch_bounds__(K1_THREADS, 2)
 assemble_fixed_kernel(int n, int nxi, const double* __restrict__ xi_arr, int grid_type,
                       double* __restrict__ P, double* __restrict__ diag)
 {
-    __shared__ double s_K[NKERN][NNODE];      // kernel values at the nodes
+    // half-kernel values [half][kernel][node]; after the combination pass [0][kernel][node] holds K(x_i, y_k)
+    extern __shared__ __align__(16) double s_dyn[];
+    double (*s_H)[NKERN][NNODE] = reinterpret_cast<double (*)[NKERN][NNODE]>(s_dyn);
+    double (*s_K)[NNODE] = s_H[0];
+    __shared__ double s_Y[NNODE][2];          // 0.5 (1 +- y/xi) at the nodes
+    __shared__ unsigned char s_live[2 * NNODE];
+    __shared__ int s_nlive;
     __shared__ double s_J[NNODE];             // Jacobians
     __shared__ double s_b[NNODE][6];          // basis rows at the nodes
     __shared__ int s_iS[NNODE];               // stencil origins (1-based)
@@ -122,13 +128,15 @@ assemble_fixed_kernel(int n, int nxi, const double* __restrict__ xi_arr, int gri
     }
     __syncthreads();
 
-    // ---- phase 1: one thread per (node, half) ----
+    // ---- phase 1a: one thread per (node, half): node, Jacobian / basis row, support class of the half ----
+    // A half kernel whose support steps rho and theta_ERBL both vanish is an exact zero when every skipped piece
+    // is finite (node_is_safe, as in K2); such halves -- about half of them -- are not evaluated, and the live
+    // ones are compacted so that whole warps drop out of the evaluation pass.
+    if (tid == 0) s_nlive = 0;
+    __syncthreads();
     {
         const int k = tid >> 1, half = tid & 1;
-        const bool active = k < NNODE;
-        double hv[NKERN];
-        double J = 1.0;
-        if (active) {
+        if (k < NNODE) {
             const int r = k / 21, q = k - 21 * r;
             const double a = s_aa[r + 1], b = s_aa[r + 2];
             const double centr = 5.0e-01 * (a + b);
@@ -136,8 +144,7 @@ assemble_fixed_kernel(int n, int nxi, const double* __restrict__ xi_arr, int gri
             const double eta = node_eta(centr, hlgth, q);
             const double y = push_forward(eta, xi, grid_type);
             if (half == 0) {
-                J = push_jacob(eta, xi, grid_type);
-                s_J[k] = J;
+                s_J[k] = push_jacob(eta, xi, grid_type);
             } else {
                 double w[6], bb[6];
 #pragma unroll
@@ -148,23 +155,45 @@ assemble_fixed_kernel(int n, int nxi, const double* __restrict__ xi_arr, int gri
             }
             const double X1 = 0.5 * (1.0 + x / xi), X2 = 0.5 * (1.0 - x / xi);
             const double Y1 = 0.5 * (1.0 + y / xi), Y2 = 0.5 * (1.0 - y / xi);
+            if (half == 0) { s_Y[k][0] = Y1; s_Y[k][1] = Y2; }
+            const bool safe = node_is_safe(X1, X2, Y1, Y2);
+            const int cls = half ? task_class(X2, Y2, safe) : task_class(X1, Y1, safe);
+            if (cls != 0) {
+                s_live[atomicAdd(&s_nlive, 1)] = (unsigned char)tid;
+            } else {
+#pragma unroll
+                for (int f = 0; f < NKERN; f++) s_H[half][f][k] = 0.0;
+            }
+        }
+    }
+    __syncthreads();
+    // ---- phase 1b: the live halves, all 22 kernels each ----
+    {
+        const int nlive = s_nlive;
+        for (int idx = tid; idx < nlive; idx += K1_THREADS) {
+            const int task = s_live[idx];
+            const int k = task >> 1, half = task & 1;
+            const double X1 = 0.5 * (1.0 + x / xi), X2 = 0.5 * (1.0 - x / xi);
+            const double Y1 = s_Y[k][0], Y2 = s_Y[k][1];
+            double hv[NKERN];
             if (half == 0) eval_half<MASK_ALL, true, 1>(X1, Y1, X2, Y2, hv, s_pre[0], s_pre[1]);
             else eval_half<MASK_ALL, true, 1>(X2, Y2, X1, Y1, hv, s_pre[1], s_pre[0]);
-        } else {
 #pragma unroll
-            for (int f = 0; f < NKERN; f++) hv[f] = 0.0;
+            for (int f = 0; f < NKERN; f++) s_H[half][f][k] = hv[f];
         }
+    }
+    __syncthreads();
+    // ---- phase 1c: K(x_i, y_k) from the two halves, in place ----
+    if (tid < NNODE) {
+        const int k = tid;
         bool fin = true;
 #pragma unroll
         for (int f = 0; f < NKERN; f++) {
-            const double other = __shfl_xor_sync(0xffffffffu, hv[f], 1);
-            if (active && half == 0) {
-                const double K = combine_halves_rt(f, hv[f], other, xi);
-                s_K[f][k] = K;
-                fin = fin && (fabs(K) <= huge_());
-            }
+            const double K = combine_halves_rt(f, s_H[0][f][k], s_H[1][f][k], xi);
+            s_K[f][k] = K;
+            fin = fin && (fabs(K) <= huge_());
         }
-        if (active && half == 0 && !(fin && fabs(J) <= huge_())) s_allfinite = 0;
+        if (!(fin && fabs(s_J[k]) <= huge_())) s_allfinite = 0;
     }
     __syncthreads();
 
@@ -1068,7 +1097,10 @@ int set_grid_variant(int eta_recip_f32, int x0_recip_f32)
 int launch_assemble_fixed(int n, int nxi, const double* xi_dev, int grid_type, double* P, double* diag, cudaStream_t st)
 {
     dim3 grid(n, nxi);
-    assemble_fixed_kernel<<<grid, K1_THREADS, 0, st>>>(n, nxi, xi_dev, grid_type, P, diag);
+    const size_t smem = 2 * sizeof(double) * NKERN * NNODE;
+    cudaError_t e = cudaFuncSetAttribute(assemble_fixed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
+    assemble_fixed_kernel<<<grid, K1_THREADS, smem, st>>>(n, nxi, xi_dev, grid_type, P, diag);
     TKB_LAUNCH_CHECK();
     return 0;
 }

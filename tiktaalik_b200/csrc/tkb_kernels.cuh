@@ -212,6 +212,48 @@ enum KernelId : int {
 constexpr unsigned MASK_ALL = (1u << NKERN) - 1u;
 __host__ __device__ constexpr unsigned bit(int k) { return 1u << k; }
 
+// ---------------------------------------------------------------------------------------
+// support classes of a half kernel (used by K1 and K2 to skip halves that are exact zeros)
+
+// every denominator / log argument that any half kernel of the node's four tasks can meet is non-zero
+// and finite, so a piece multiplied by a vanishing support step is an exact zero (not 0*Inf = NaN).
+// (a1, a2) = (0.5 (1 + x/xi), 0.5 (1 - x/xi)), (b1, b2) the same for y.
+TKB_DEV bool node_is_safe(double a1, double a2, double b1, double b2)
+{
+    const double big = huge_();
+    bool ok = (fabs(a1) <= big) && (fabs(a2) <= big) && (fabs(b1) <= big) && (fabs(b2) <= big);
+    const double v[4] = { a1, a2, b1, b2 };
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const double c = 1.0 - v[k];                 // Xbar / Ybar / 1 - Xo
+        ok = ok && (v[k] != 0.0) && (c != 0.0) && (1.0 - c != 0.0);
+    }
+    // pairs (X, Y) that appear as Y - X, Ybar - Xbar, Y - Xo, Ybar - (1 - Xo), Y - Xbar, Ybar - Xbb, Y/X - 1:
+    // any first-argument value against any second-argument value, in both directions
+    const double eps4 = 4.0 * eps_();
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int j = 2; j < 4; j++) {
+            const double p = v[i], q = v[j];
+            const double pb = 1.0 - p, qb = 1.0 - q;
+            ok = ok && (fabs(q - p) > eps4 * fabs(p)) && (fabs(p - q) > eps4 * fabs(q)) && (qb != pb) &&
+                 (q != pb) && (p != qb) && (qb != 1.0 - pb) && (pb != 1.0 - qb);
+        }
+    ok = ok && (a2 != a1) && (b2 != b1);             // Yo - Xo of the non-singlet halves: (a1,a2) vs (b1,b2) handled above
+    return ok;
+}
+
+// support class of the half kernel at (X, Y): 2 full, 1 erbl-only, 0 dead (see half_class)
+TKB_DEV int task_class(double X, double Y, bool safe)
+{
+    const double r = X / Y;
+    const double omr = 1.0 - r;
+    if (rho_step(r, omr, Y) != 0.0) return 2;
+    if (!safe || omr == 0.0 || r == 0.0) return 2;
+    return (theta_step(X) * theta_step(1.0 - X) != 0.0) ? 1 : 0;
+}
+
 // How the two halves combine into K(x,y,xi) (kernels_lo.f90 / kernels_nlo.f90 wrappers):
 //   sign  +1: K = h(X1,Y1) + h(X2,Y2);  -1: K = h(X1,Y1) - h(X2,Y2);  -2: K = -h(X1,Y1) + h(X2,Y2)
 //   pref  colour factor c in  K = c*0.5*K/xi  (LO) or K = 0.5*K/xi (NLO, c = 0 marks "no colour")
