@@ -1247,9 +1247,10 @@ static int launch_pipe_one(int c, int n, int nxi, const double* xi_dev, int grid
         cudaStreamSynchronize(st);
         unsigned long long h[16];
         cudaMemcpyFromSymbol(h, g_k2stats, sizeof h);
-        fprintf(stderr, "K2 pipe stats KID %d: bookkeeper per round: wait-values %.0f, bookkeeping %.0f, wait-REQ %.0f cyc (%llu rounds) | evaluators per round: wait-requests %.0f, work %.0f cyc (%llu rounds)\n",
+        fprintf(stderr, "K2 pipe stats KID %d: bookkeeper per round: wait-values %.0f, bookkeeping %.0f, wait-REQ %.0f cyc (%llu rounds) | evaluators per round: wait-requests %.0f, work %.0f cyc (%llu rounds) | block lifetime %.3g cyc, of which draining after the queue ran dry %.3g (%.1f %%)\n",
                 KID, h[3] ? (double)h[0] / h[3] : 0., h[3] ? (double)h[1] / h[3] : 0., h[3] ? (double)h[2] / h[3] : 0., h[3],
-                h[6] ? (double)h[4] / h[6] : 0., h[6] ? (double)h[5] / h[6] : 0., h[6]);
+                h[6] ? (double)h[4] / h[6] : 0., h[6] ? (double)h[5] / h[6] : 0., h[6], (double)h[7], (double)h[15],
+                h[7] ? 100.0 * (double)h[15] / (double)h[7] : 0.0);
         unsigned long long z[16] = { 0 };
         cudaMemcpyToSymbol(g_k2stats, z, sizeof z);
     }

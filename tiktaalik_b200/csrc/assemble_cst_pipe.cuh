@@ -30,6 +30,7 @@ struct QPipeShared {
     unsigned short live[2][2][QG * 84]; // per group and direction: full tasks from the front, erbl-only from the back
     int nfull[2][2], nerbl[2][2];
     int next[2];                        // E phase: next 32-task chunk of the group
+    long long t_exh;                    // TKB_K2_STATS: clock at which this block first found the queue empty
     int act[2][8];                      // per group and bookkeeping warp: it still has a running instance
 };
 
@@ -82,6 +83,7 @@ assemble_cst_pipe_kernel(int c, int n, int nxi, const double* __restrict__ xi_ar
     const int tid = threadIdx.x;
     const unsigned long long total = (unsigned long long)nxi * n * 3ULL;
     if (tid < 2 * QG) sh.slot[tid].nint = 0;
+    if (tid == 0) sh.t_exh = 0;
     if (tid < 2) { sh.nfull[tid][0] = sh.nfull[tid][1] = 0; sh.nerbl[tid][0] = sh.nerbl[tid][1] = 0; sh.next[tid] = 0; }
     __syncthreads();
 
@@ -134,6 +136,9 @@ assemble_cst_pipe_kernel(int c, int n, int nxi, const double* __restrict__ xi_ar
                     }
                     if (!exhausted) {
                         const unsigned long long inst = atomicAdd(counter, 1ULL);
+#ifdef TKB_K2_STATS
+                        if (inst >= total && sh.t_exh == 0) sh.t_exh = clock64();
+#endif
                         if (inst >= total) exhausted = true;
                         else {
                             const int sub = (int)(inst % 3ULL);
@@ -192,6 +197,9 @@ assemble_cst_pipe_kernel(int c, int n, int nxi, const double* __restrict__ xi_ar
 
     // ======================= evaluators =======================
     const int etid = tid - NBK;
+#ifdef TKB_K2_STATS
+    const long long tk0_ = clock64();
+#endif
     int alive = 3;
     for (int g = 0; alive != 0; g ^= 1) {
         if (!((alive >> g) & 1)) continue;
@@ -317,6 +325,13 @@ assemble_cst_pipe_kernel(int c, int n, int nxi, const double* __restrict__ xi_ar
         }
 #endif
     }
+#ifdef TKB_K2_STATS
+    if (etid == 0) {
+        const long long now_ = clock64();
+        atomicAdd(&g_k2stats[7], (unsigned long long)(now_ - tk0_));                              // block lifetime
+        atomicAdd(&g_k2stats[15], (unsigned long long)(sh.t_exh ? now_ - sh.t_exh : 0));           // of which after the queue ran dry
+    }
+#endif
 }
 
 }  // namespace tkb
