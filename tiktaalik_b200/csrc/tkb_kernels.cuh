@@ -244,14 +244,18 @@ TKB_DEV bool node_is_safe(double a1, double a2, double b1, double b2)
     return ok;
 }
 
-// support class of the half kernel at (X, Y): 2 full, 1 erbl-only, 0 dead (see half_class)
+// support class of the half kernel at (X, Y): 2 full, 1 erbl-only, 0 dead.
+// The evaluation forms r = X / Y, rho_step(r, 1 - r, Y) = theta(1 - r) theta(r) sign(Y) and
+// erbl_step = theta(X) theta(1 - X) with theta(0) = 1/2.  For a safe node (X, Y finite, non-zero, X != Y:
+// node_is_safe) the class follows from the operands without the division: a correctly rounded quotient has
+// the sign of X Y and is <= 1 exactly when |X| <= |Y| (two different doubles differ by more than half an ulp of
+// their quotient, so it cannot round to 1), hence rho != 0  <=>  sign X = sign Y and |X| <= |Y|; r = 0 or
+// 1 - r = 0 would need X = 0 or X = Y.  An unsafe node is always evaluated in full.
 TKB_DEV int task_class(double X, double Y, bool safe)
 {
-    const double r = X / Y;
-    const double omr = 1.0 - r;
-    if (rho_step(r, omr, Y) != 0.0) return 2;
-    if (!safe || omr == 0.0 || r == 0.0) return 2;
-    return (theta_step(X) * theta_step(1.0 - X) != 0.0) ? 1 : 0;
+    if (!safe) return 2;
+    if (((X < 0.0) == (Y < 0.0)) && fabs(X) <= fabs(Y)) return 2;
+    return (X >= 0.0 && 1.0 - X >= 0.0) ? 1 : 0;
 }
 
 // How the two halves combine into K(x,y,xi) (kernels_lo.f90 / kernels_nlo.f90 wrappers):
