@@ -218,42 +218,57 @@ assemble_cst_pipe_kernel(int c, int n, int nxi, const double* __restrict__ xi_ar
         }
         // ---- N + C: node arguments, support classes, compaction (see assemble_cst_batched.cuh); the tasks are
         // listed per direction so that a warp evaluates one direction (one set of pre-computed values) ----
-        for (int e = etid; e < QG * 42; e += NE) {
-            const int s = g * QG + e / 42, node = e % 42;
+        // (warp-aggregated compaction: one shared-memory atomic per warp and list instead of one per thread)
+        for (int e0 = 0; e0 < QG * 42; e0 += NE) {
+            const int e = e0 + etid;
+            const bool inr = e < QG * 42;
+            const int s = g * QG + (inr ? e / 42 : 0), node = inr ? e % 42 : 0;
             const QSlot& S = sh.slot[s];
-            if (node >= 21 * S.nint) continue;
-            const int iv = node / 21, q = node - 21 * iv;
-            const double a = iv ? S.a2 : S.a1, b = iv ? S.b2 : S.b1;
-            const double centr = 5.0e-01 * (a + b);
-            const double hlgth = 5.0e-01 * (b - a);
-            const double y = node_eta(centr, hlgth, q);
-            const double t = y / S.xi;
-            const double yy1 = 0.5 * (1.0 + t), yy2 = 0.5 * (1.0 - t);
-            sh.ny[s][node][0] = yy1;
-            sh.ny[s][node][1] = yy2;
-            const double xx1 = S.xx1, xx2 = S.xx2;
-            const bool safe = node_is_safe(xx1, xx2, yy1, yy2);
-            int cls[4];
-            cls[0] = task_class(xx1, yy1, safe);       // dir 0 (K(x,y)), half 0
-            cls[1] = task_class(xx2, yy2, safe);       // dir 0, half 1
-            cls[2] = task_class(yy1, xx1, safe);       // dir 1 (K(y,x)), half 0
-            cls[3] = task_class(yy2, xx2, safe);       // dir 1, half 1
+            const bool act = inr && node < 21 * S.nint;
+            int cls[4] = { 0, 0, 0, 0 };
+            if (act) {
+                const int iv = node / 21, q = node - 21 * iv;
+                const double a = iv ? S.a2 : S.a1, b = iv ? S.b2 : S.b1;
+                const double centr = 5.0e-01 * (a + b);
+                const double hlgth = 5.0e-01 * (b - a);
+                const double y = node_eta(centr, hlgth, q);
+                const double t = y / S.xi;
+                const double yy1 = 0.5 * (1.0 + t), yy2 = 0.5 * (1.0 - t);
+                sh.ny[s][node][0] = yy1;
+                sh.ny[s][node][1] = yy2;
+                const double xx1 = S.xx1, xx2 = S.xx2;
+                const bool safe = node_is_safe(xx1, xx2, yy1, yy2);
+                cls[0] = task_class(xx1, yy1, safe);       // dir 0 (K(x,y)), half 0
+                cls[1] = task_class(xx2, yy2, safe);       // dir 0, half 1
+                cls[2] = task_class(yy1, xx1, safe);       // dir 1 (K(y,x)), half 0
+                cls[3] = task_class(yy2, xx2, safe);       // dir 1, half 1
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                if (!HAS_ERBL && cls[k] == 1) cls[k] = 0;
-                if (cls[k] == 0) sh.hv[s][4 * node + k] = 0.0;
+                for (int k = 0; k < 4; k++) {
+                    if (!HAS_ERBL && cls[k] == 1) cls[k] = 0;
+                    if (cls[k] == 0) sh.hv[s][4 * node + k] = 0.0;
+                }
             }
+            const int elane_ = etid & 31;
+            const unsigned lt = (1u << elane_) - 1u;
 #pragma unroll
             for (int d = 0; d < 2; d++) {
-                const int nf = (cls[2 * d] == 2) + (cls[2 * d + 1] == 2), ne = (cls[2 * d] == 1) + (cls[2 * d + 1] == 1);
-                int of = nf ? atomicAdd(&sh.nfull[g][d], nf) : 0;
-                int oe = ne ? atomicAdd(&sh.nerbl[g][d], ne) : 0;
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const int k = 2 * d + h;
-                    const unsigned short id = (unsigned short)((s - g * QG) * 168 + 4 * node + k);
-                    if (cls[k] == 2) sh.live[g][d][of++] = id;
-                    if (cls[k] == 1) sh.live[g][d][QG * 84 - 1 - (oe++)] = id;
+                const unsigned f0 = __ballot_sync(0xffffffffu, cls[2 * d] == 2), f1 = __ballot_sync(0xffffffffu, cls[2 * d + 1] == 2);
+                const unsigned r0 = HAS_ERBL ? __ballot_sync(0xffffffffu, cls[2 * d] == 1) : 0u;
+                const unsigned r1 = HAS_ERBL ? __ballot_sync(0xffffffffu, cls[2 * d + 1] == 1) : 0u;
+                const int nf = __popc(f0) + __popc(f1), ne = __popc(r0) + __popc(r1);
+                int bf = 0, be = 0;
+                if (elane_ == 0) {
+                    if (nf) bf = atomicAdd(&sh.nfull[g][d], nf);
+                    if (ne) be = atomicAdd(&sh.nerbl[g][d], ne);
+                }
+                bf = __shfl_sync(0xffffffffu, bf, 0);
+                be = __shfl_sync(0xffffffffu, be, 0);
+                const unsigned short id0 = (unsigned short)((s - g * QG) * 168 + 4 * node + 2 * d);
+                if (cls[2 * d] == 2) sh.live[g][d][bf + __popc(f0 & lt)] = id0;
+                if (cls[2 * d + 1] == 2) sh.live[g][d][bf + __popc(f0) + __popc(f1 & lt)] = id0 + 1;
+                if (HAS_ERBL) {
+                    if (cls[2 * d] == 1) sh.live[g][d][QG * 84 - 1 - (be + __popc(r0 & lt))] = id0;
+                    if (cls[2 * d + 1] == 1) sh.live[g][d][QG * 84 - 1 - (be + __popc(r0) + __popc(r1 & lt))] = id0 + 1;
                 }
             }
         }
