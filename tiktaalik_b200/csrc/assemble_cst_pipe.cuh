@@ -34,6 +34,16 @@ struct QPipeShared {
     int act[2][8];                      // per group and bookkeeping warp: it still has a running instance
 };
 
+// which entries of the per-instance table (PRE_*) the half kernel of one constant reads (the N_* flags of eval_half)
+template <int KID>
+__host__ __device__ constexpr unsigned qp_pre_need()
+{
+    return (KID == K_NSN) ? 0u
+         : (KID == K_V1GGN || KID == K_A1GGN) ? ((1u << PRE_L) | (1u << PRE_LB))
+         : (KID == K_NSP || KID == K_NSM) ? ((1u << PRE_L) | (1u << PRE_LB) | (1u << PRE_D) | (1u << PRE_DB))
+         : 0x1fu;
+}
+
 enum { QP_BAR_REQ0 = 1, QP_BAR_REQ1 = 2, QP_BAR_VAL0 = 3, QP_BAR_VAL1 = 4, QP_BAR_EV = 5 };
 
 // barrier ids are immediates so that ptxas reserves only the barriers in use (a register id reserves all 16)
@@ -273,10 +283,13 @@ assemble_cst_pipe_kernel(int c, int n, int nxi, const double* __restrict__ xi_ar
             }
         }
         // one-argument transcendental values of the instances that start in this round (nint == 1)
-        for (int e = etid; e < QG * 2 * PRE_N; e += NE) {
-            const int s = g * QG + e / (2 * PRE_N), v = e % (2 * PRE_N);
-            const QSlot& S = sh.slot[s];
-            if (S.nint == 1) sh.pre[s][v / PRE_N][v % PRE_N] = pre_value(v % PRE_N, (v / PRE_N) ? S.xx2 : S.xx1);
+        if (qp_pre_need<KID>() != 0u) {
+            for (int e = etid; e < QG * 2 * PRE_N; e += NE) {
+                const int s = g * QG + e / (2 * PRE_N), v = e % (2 * PRE_N);
+                const QSlot& S = sh.slot[s];
+                if (S.nint == 1 && ((qp_pre_need<KID>() >> (v % PRE_N)) & 1u))
+                    sh.pre[s][v / PRE_N][v % PRE_N] = pre_value(v % PRE_N, (v / PRE_N) ? S.xx2 : S.xx1);
+            }
         }
         qp_bar_sync(QP_BAR_EV, NE);
 
