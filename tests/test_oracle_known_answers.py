@@ -6,7 +6,10 @@ be built here (no Fortran compiler), so the restatement is pinned by:
   * polynomiality of every kernel function (moments int dx x^m K(x,y,xi) are polynomials in y:
     any mistyped coefficient in kernels_lo/kernels_nlo breaks the ERBL/DGLAP cancellation),
   * the momentum sum rule tying the V-type QQ, GQ, QG kernels and the explicit constants,
-  * alpha_s anchors, block identities, and bit-equality of the two oracle loop nests.
+  * alpha_s anchors, block identities, and bit-equality of the two oracle loop nests,
+  * the forward limit xi -> 0 of every V-type kernel function (LO and NLO, non-singlet and all singlet
+    entries, nfl^0 and nfl^1 parts), of the A-type LO functions and of the A-type NLO pure-singlet function
+    against the DGLAP splitting functions of the literature (tests/splitting_functions.py), to 1e-8 .. 1e-5.
 """
 import warnings
 
@@ -191,3 +194,62 @@ def test_ofast_variant_switches_move_a_sixth_of_the_nodes(tko):
         assert np.array_equal(tko.grid_nodes(160, 0.1, 1), x0)          # x0 switch does not touch the nodes
     finally:
         tko.set_variant(0, 0)
+
+
+# --------------------------------------------------------------------------------------------
+# forward limit: xi -> 0 must give the DGLAP splitting functions of the literature (tests/splitting_functions.py)
+#
+# Conventions of the reference: a = alpha_s / (2 pi) = 2 a_s, so K0 = P0 / 2 and K1 = P1 / 4; the gluon GPD becomes
+# x g(x), so for 0 < x < y, z = x / y:   K_qq = P_qq(z) / y,  K_qG = P_qg(z) / y^2,  K_Gq = (x / y) P_gq(z),
+# K_GG = (x / y^2) P_gg(z); the singlet quark kernels are per flavour (nfl multiplies them in matevo.f90:370-472).
+
+def _forward_limit(tko, names, x, y):
+    """Richardson extrapolation in xi^2 (the V-type gluon kernels lose ~1/xi^4 digits, so xi stays >= 0.01)"""
+    if isinstance(names, str):
+        names = (names,)
+    f = [sum(tko.kernel(n, x, y, s) for n in names) for s in (0.04, 0.02, 0.01)]
+    r = [(4 * f[1] - f[0]) / 3, (4 * f[2] - f[1]) / 3]
+    return (16 * r[1] - r[0]) / 15
+
+
+FWD_POINTS = [(0.2, 0.5), (0.45, 0.6), (0.3, 0.9), (0.1, 0.8)]
+
+
+@pytest.mark.parametrize("x,y", FWD_POINTS)
+def test_forward_limit_non_singlet_nlo(tko, x, y):
+    import splitting_functions as sf
+    z, xi = x / y, 1e-5                      # the non-singlet kernels are well conditioned at small xi
+    assert abs(tko.kernel("K0_qq_pls", x, y, xi) / (sf.P0_qq(z) / y) - 1) < 2e-9
+    for name, sign in (("KV1_NSp_pls", +1), ("KV1_NSm_pls", -1)):
+        assert abs(tko.kernel(name, x, y, xi) / (sf.P1_ns(z, sign, 0) / 4 / y) - 1) < 2e-8, name
+    nfl = (sf.P1_ns(z, +1, 1) - sf.P1_ns(z, +1, 0)) / 4 / y
+    assert abs(tko.kernel("KV1_NS_pls_nfl", x, y, xi) / nfl - 1) < 2e-8
+    assert tko.kernel("KV1_NSm_pls_nfl", x, y, xi) == tko.kernel("KV1_NS_pls_nfl", x, y, xi)
+
+
+@pytest.mark.parametrize("x,y", FWD_POINTS)
+def test_forward_limit_singlet_lo_and_nlo(tko, x, y):
+    import splitting_functions as sf
+    z = x / y
+    tol = 5e-5 if x < 0.15 else 2e-6         # the extrapolation error grows like (xi / x)^6
+    cases = [
+        # V type = A type + (V - A) pieces at LO (matevo.f90:339-403)
+        (("KA0_qG_reg", "KVmA0_qG_reg"), sf.P0_qg(z, 1) / 2 / y ** 2),
+        (("KA0_Gq_reg", "KVmA0_Gq_reg"), sf.P0_gq(z) / 2 * (x / y)),
+        (("KA0_GG_pls", "KVmA0_GG_reg"), sf.P0_gg(z) / 2 * (x / y) / y),
+        ("KA0_qG_reg", sf.dP0_qg(z, 1) / 2 / y ** 2),
+        ("KA0_Gq_reg", sf.dP0_gq(z) / 2 * (x / y)),
+        ("KA0_GG_pls", sf.dP0_gg(z) / 2 * (x / y) / y),
+        # NLO, V type: all five singlet entries, nfl^0 and nfl^1 parts
+        ("KV1_qq_reg", sf.P1_ps(z, 1) / 4 / y),
+        ("KV1_qG_reg", sf.P1_qg(z, 1) / 4 / y ** 2),
+        ("KV1_Gq_reg", sf.P1_gq(z, 0) / 4 * (x / y)),
+        ("KV1_Gq_reg_nfl", (sf.P1_gq(z, 1) - sf.P1_gq(z, 0)) / 4 * (x / y)),
+        ("KV1_GG_pls", sf.P1_gg(z, 0) / 4 * (x / y) / y),
+        ("KV1_GG_pls_nfl", (sf.P1_gg(z, 1) - sf.P1_gg(z, 0)) / 4 * (x / y) / y),
+        # NLO, A type: pure singlet
+        ("KA1_qq_reg", sf.dP1_ps(z, 1) / 4 / y),
+    ]
+    for names, ref in cases:
+        got = _forward_limit(tko, names, x, y)
+        assert abs(got / ref - 1) < tol, (names, got, ref)
