@@ -8,8 +8,9 @@
  * PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures for this
  * path and it cannot be built here (no Fortran compiler),
  * so this restatement is pinned only by reference-independent known-answer tests
- * (mpmath dilogarithm, SciPy QUADPACK, block identities, sum rules); see
- * tests/test_oracle_*.py and DESIGN.md.
+ * (mpmath dilogarithm, SciPy QUADPACK, block identities, polynomiality, sum rules, and
+ * the forward limit xi -> 0 against the published LO/NLO DGLAP splitting functions); see
+ * tests/test_oracle_known_answers.py, tests/splitting_functions.py and DESIGN.md.
  */
 #ifndef TKO_H
 #define TKO_H
