@@ -253,3 +253,22 @@ def test_forward_limit_singlet_lo_and_nlo(tko, x, y):
     for names, ref in cases:
         got = _forward_limit(tko, names, x, y)
         assert abs(got / ref - 1) < tol, (names, got, ref)
+
+
+# --------------------------------------------------------------------------------------------
+# conformal moments: at LO the moments c_n(x, xi) = xi^n C_n^{3/2}(x / xi) renormalise multiplicatively for
+# every xi, with the forward anomalous dimensions (Efremov-Radyushkin / Brodsky-Lepage; BFM sec. 2):
+#   int dx [c_n(x) - c_n(y)] K0_qq(x, y, xi) = -(gamma_n / 2) c_n(y),  gamma_n = CF (4 S_1(n+1) - 3 - 2 / ((n+1)(n+2)))
+# This fixes the xi dependence of the LO quark kernel in all regions (ERBL, DGLAP, y of either sign).
+
+@pytest.mark.parametrize("xi", [0.3, 0.7])
+def test_lo_conformal_moments_are_eigenfunctions(tko, xi):
+    gegenbauer = pytest.importorskip("scipy.special").gegenbauer
+    CF = 4.0 / 3.0
+    for n in range(1, 6):
+        Cn = gegenbauer(n, 1.5)
+        c = lambda x: xi ** n * Cn(x / xi)
+        gamma = CF * (4 * sum(1.0 / k for k in range(1, n + 2)) - 3 - 2.0 / ((n + 1) * (n + 2)))
+        for y in (0.15, 0.55, -0.4):
+            val = _xint(lambda x: (c(x) - c(y)) * tko.kernel("K0_qq_pls", x, y, xi), y, xi)
+            assert abs(val + 0.5 * gamma * c(y)) < 1e-10 * max(1.0, abs(c(y))), (n, y, val, -0.5 * gamma * c(y))
