@@ -317,6 +317,7 @@ def main():
             "roofline": {"bound": "fp64", "kernel": "K2, the QAGS constants: assemble_cst_pipe_kernel<KID> x 7 launches; duration = the assembly span, which also contains the overlapped fixed-quadrature kernel K1",
                          "achieved": k2_tflops, "peak": peak.value, "unit": "TFLOP/s",
                          "frac": k2_tflops / peak.value if peak.value else None, "traffic": fpe.get("traffic_bytes"),
+                         "traffic_source": fpe.get("traffic_source"),
                          "peak_source": "DFMA microbenchmark measured in this run (tkb_fp64_peak); MEASURED_PEAKS.json "
                                         "has HBM and bf16 only",
                          "share_of_step": stage[1] / (ms / args.steps),
