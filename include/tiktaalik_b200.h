@@ -80,6 +80,22 @@ int tkb_alpha(int n, const double* q2_host, double* out_host);
 int tkb_apply(int m, int nxi, int nq2, int64_t S, const double* M_dev, const double* g_dev, int64_t ldg,
               double* out_dev, void* stream);
 
+/* replaces evolve_fixed_flavor (tiktaalik/evolution.py:495-514) = make_evo_basis (:435-462) + three applications
+ * (:507-509) + make_flv_basis (:465-492) + zero padding (:532-540) for one threshold segment at a fixed number of
+ * flavours nfl, fused: one decoupling kernel, three applications, one recoupling kernel.
+ *   gpd_dev  [F][nx][nxi][S]       flavour basis, row 0 gluon, rows 1.. quarks (u, d, s, ...); missing rows count as zero
+ *   M_*_dev  [xi][Q2][m][m]        the segment's singlet (m = 2 nx), plus-type and minus-type non-singlet matrices
+ *   out_dev  [Fout][nx][nxi][S][ldq]  receives the nq2 - skip last Q2 points of the segment in columns q0, q0 + 1, ...
+ *                                  (skip = 1 drops the segment's first point, which repeats its input); rows > nfl are zero
+ *   tpls_host, tpls_inv_host       the nfl x nfl matrix (u+, d+, ...) -> (Sigma, T3, T8, ...) of evolution.py:517-529 and its
+ *                                  inverse (np.linalg.inv in the reference), row-major, host memory
+ *   work_dev                       tkb_evolve_workspace(...) doubles of device scratch */
+int64_t tkb_evolve_workspace(int nx, int nxi, int nq2, int64_t S, int nfl);
+int tkb_evolve_fixed_flavor(int nx, int nxi, int nq2, int64_t S, int nfl, int F, int Fout, const double* tpls_host,
+                            const double* tpls_inv_host, const double* M_sg_dev, const double* M_nsp_dev,
+                            const double* M_nsm_dev, const double* gpd_dev, double* out_dev, int64_t ldq, int q0, int skip,
+                            double* work_dev, void* stream);
+
 /* replaces hu_wrap ... hd_sea_wrap (f90wrap/model.f90:16-158 -> model/gk.f90:75-241): the GK model GPD
  * out[ix][ixi][it] = H_which(x[ix], xi[ixi], t[it]); which = 0 Hu, 1 Hd, 2 Hs, 3 Hg, 4 Hu_val, 5 Hd_val,
  * 6 Hu_sea, 7 Hd_sea.  Input generator of the examples, not part of the timed path. */

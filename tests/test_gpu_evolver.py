@@ -167,3 +167,18 @@ def test_gk_model_on_device_bit_identical(tk, tko):
     assert np.array_equal(s, tko.H_singlet(x, xi, t))
     # scalars are accepted like in the reference (examples/examples.py:46)
     assert tuple(tk.model.Hu(x, 0.5, t=0).shape) == (40, 1, 1)
+
+
+@pytest.mark.parametrize("nfl,F,extra", [(3, 4, (5,)), (4, 6, (2, 3)), (5, 4, ()), (4, 3, (40,))])
+def test_fused_fixed_flavor_step_equals_the_unfused_pipeline(tk, nfl, F, extra):
+    """csrc/evolve.cu against the reference-shaped sequence of tensor operations (evolution.py:435-514)"""
+    nx, xis = 12, np.array([0.1, 0.3, 0.6])
+    tk.matrices.initialize_kernels(nx, xis, grid_type=2)
+    tk.matrices.initialize_evolution_matrices(tk.matrices.Q2space(4.0, 40.0, 5), nlo=True)
+    M_SG, M_p, M_m = tk.matrices.matrix_VSG(), tk.matrices.matrix_VNS(1), tk.matrices.matrix_VNS(-1)
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    g = torch.rand((F, nx, len(xis)) + extra, generator=gen, dtype=torch.float64, device="cuda") - 0.3
+    a = tk.evolution.evolve_fixed_flavor(g, M_SG, M_p, M_m, nfl=nfl)
+    b = tk.evolution.evolve_fixed_flavor_unfused(g, M_SG, M_p, M_m, nfl=nfl)
+    assert tuple(a.shape) == tuple(b.shape)
+    assert torch.allclose(a, b, rtol=1e-12, atol=1e-13 * float(b.abs().max()))

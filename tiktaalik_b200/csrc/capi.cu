@@ -489,6 +489,25 @@ int tkb_apply(int m, int nxi, int nq2, int64_t S, const double* M_dev, const dou
     return launch_apply(m, nxi, nq2, S, M_dev, g_dev, ldg, out_dev, (cudaStream_t)stream);
 }
 
+int64_t tkb_evolve_workspace(int nx, int nxi, int nq2, int64_t S, int nfl)
+{
+    if (nx < 1 || nxi < 1 || nq2 < 1 || S < 0 || nfl < 1 || nfl > 5) return -1;
+    return (int64_t)evolve_workspace_doubles(nx, nxi, nq2, S, nfl);
+}
+
+int tkb_evolve_fixed_flavor(int nx, int nxi, int nq2, int64_t S, int nfl, int F, int Fout, const double* tpls_host,
+                            const double* tpls_inv_host, const double* M_sg_dev, const double* M_nsp_dev,
+                            const double* M_nsm_dev, const double* gpd_dev, double* out_dev, int64_t ldq, int q0, int skip,
+                            double* work_dev, void* stream)
+{
+    if (nx < 1 || nxi < 1 || nq2 < 1 || S < 0 || nfl < 1 || nfl > 5 || F < 1 || Fout < nfl + 1 || Fout > 6 || skip < 0 ||
+        skip > nq2 || q0 < 0 || ldq < q0 + (nq2 - skip) || !tpls_host || !tpls_inv_host || !M_sg_dev || !M_nsp_dev ||
+        !M_nsm_dev || !gpd_dev || !out_dev || !work_dev)
+        return set_error("tkb_evolve_fixed_flavor: bad arguments");
+    return launch_evolve_fixed_flavor(nx, nxi, nq2, S, nfl, F, Fout, tpls_host, tpls_inv_host, M_sg_dev, M_nsp_dev, M_nsm_dev,
+                                      gpd_dev, out_dev, ldq, q0, skip, work_dev, (cudaStream_t)stream);
+}
+
 int tkb_gk(int which, int nx, int nxi, int nt, const double* x_dev, const double* xi_dev, const double* t_dev,
            double* out_dev, void* stream)
 {

@@ -57,6 +57,11 @@ int launch_scale_add(size_t count, double a, double a2, int nlo, const double* K
 int launch_dfma_peak(int blocks, int iters, double* scratch, cudaStream_t st);
 
 // apply.cu
+size_t evolve_workspace_doubles(int n, int nxi, int nq, int64_t S, int nfl);
+int launch_evolve_fixed_flavor(int n, int nxi, int nq, int64_t S, int nfl, int F, int Fout, const double* T,
+                               const double* N, const double* M_sg, const double* M_nsp, const double* M_nsm,
+                               const double* gpd, double* out, int64_t ldq, int q0, int skip, double* work,
+                               cudaStream_t st);
 int launch_apply(int m, int nxi, int nq2, int64_t S, const double* M, const double* g, int64_t ldg,
                  double* out, cudaStream_t st);
 

@@ -129,22 +129,34 @@ class Evolver:
         assert(self.nx  == gpd_grid.shape[1])
         assert(self.nxi == gpd_grid.shape[2])
         assert( (gpd_type=='V') or (gpd_type=='A') )
-        new_gpd = gpd_grid.clone()[...,None]
-        nfl = new_gpd.shape[0] - 1
-        if(nfl < self.nfl):
-            new_gpd = add_pad(new_gpd, self.nfl - nfl)
+        # Segments: (below mc2, nfl=3), (mc2..mb2, nfl=4), (.. Q2f, nfl at Q2f); each starts from the last Q2 point of
+        # the previous one and contributes all its Q2 points but the first (reference: evolution.py:121-150).
+        segs = []
         if(self.pass_charm):
-            M_SG, M_NSp, M_NSm = self._triplet("mc2", gpd_type, nlo)
-            added_gpd = evolve_fixed_flavor(new_gpd[...,-1], M_SG, M_NSp, M_NSm, nfl=3)
-            new_gpd = torch.cat((new_gpd, added_gpd[...,1:]), dim=-1)
+            segs.append(("mc2", 3))
         if(self.pass_bottom):
-            M_SG, M_NSp, M_NSm = self._triplet("mb2", gpd_type, nlo)
-            added_gpd = evolve_fixed_flavor(new_gpd[...,-1], M_SG, M_NSp, M_NSm, nfl=4)
-            new_gpd = torch.cat((new_gpd, added_gpd[...,1:]), dim=-1)
-        M_SG, M_NSp, M_NSm = self._triplet("Q2f", gpd_type, nlo)
-        nfl = get_nfl(self.Q2f)
-        added_gpd = evolve_fixed_flavor(new_gpd[...,-1], M_SG, M_NSp, M_NSm, nfl=nfl)
-        new_gpd = torch.cat((new_gpd, added_gpd[...,1:]), dim=-1)
+            segs.append(("mb2", 4))
+        segs.append(("Q2f", get_nfl(self.Q2f)))
+        trip = [self._triplet(seg, gpd_type, nlo) for seg, _ in segs]
+        F, nx, nxi = (int(v) for v in gpd_grid.shape[:3])
+        extra = tuple(int(v) for v in gpd_grid.shape[3:])
+        S = 1
+        for e in extra:
+            S *= e
+        Fout = max(F, self.nfl + 1)
+        nq_tot = 1 + sum(int(t[0].shape[3]) - 1 for t in trip)
+        out = torch.empty((Fout, nx, nxi, S, nq_tot), dtype=torch.float64, device=gpd_grid.device)
+        cur = torch.zeros((Fout, nx, nxi, S), dtype=torch.float64, device=gpd_grid.device)
+        cur[:F] = gpd_grid.reshape(F, nx, nxi, S)
+        out[..., 0] = cur
+        q0 = 1
+        for (seg, nfl), (M_SG, M_NSp, M_NSm) in zip(segs, trip):
+            nq = int(M_SG.shape[3])
+            if S > 0 and nq > 1:
+                _fused_fixed_flavor(cur, M_SG, M_NSp, M_NSm, nfl, out, q0, 1)
+            q0 += nq - 1
+            cur = out[..., q0 - 1].contiguous()
+        new_gpd = out.reshape((Fout, nx, nxi) + extra + (nq_tot,))
         return new_gpd
 
     ## ~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~
@@ -296,9 +308,51 @@ def make_flv_basis(sg_grid, t_grid, qmin_grid, nfl):
     return gpd_grid
 
 
+def _storage(M):
+    """[xi][Q2][i][j] storage of a matrix of logical shape (m, m, nxi, nQ2); no copy for what the getters return"""
+    st = M.permute(2, 3, 0, 1)
+    return st if st.is_contiguous() else st.contiguous()
+
+
+def _fused_fixed_flavor(gpd_in, M_SG, M_NSp, M_NSm, nfl, out, q0, skip):
+    """tkb_evolve_fixed_flavor: gpd_in (F, nx, nxi, S) contiguous -> out[:, :, :, :, q0 : q0 + nQ2 - skip]"""
+    import ctypes as C
+    L = _lib.lib()
+    F, nx, nxi, S = (int(v) for v in gpd_in.shape)
+    nq = int(M_SG.shape[3])
+    T = np.ascontiguousarray(Tpls_matrix(nfl), dtype=np.float64)
+    N = np.ascontiguousarray(np.linalg.inv(T), dtype=np.float64)
+    sg, nsp, nsm = _storage(M_SG), _storage(M_NSp), _storage(M_NSm)
+    nwork = int(L.tkb_evolve_workspace(nx, nxi, nq, S, nfl))
+    work = torch.empty((max(nwork, 1),), dtype=torch.float64, device=gpd_in.device)
+    _lib.check(L.tkb_evolve_fixed_flavor(nx, nxi, nq, S, nfl, F, int(out.shape[0]), T.ctypes.data_as(_lib._dp),
+                                         N.ctypes.data_as(_lib._dp), _lib.ptr(sg), _lib.ptr(nsp), _lib.ptr(nsm),
+                                         _lib.ptr(gpd_in), _lib.ptr(out), int(out.shape[-1]), int(q0), int(skip),
+                                         _lib.ptr(work), _lib.stream_ptr()))
+
+
 def evolve_fixed_flavor(gpd_grid, M_SG, M_NSp, M_NSm, nfl=4):
     ''' Evolve a flavour-basis grid with given singlet / non-singlet matrices at a fixed number of
-    flavours: decouple, apply, recouple (reference: evolution.py:495-514). '''
+    flavours: decouple, apply, recouple (reference: evolution.py:495-514).  One fused library call
+    (csrc/evolve.cu); evolve_fixed_flavor_unfused is the same pipeline as separate tensor operations. '''
+    gpd_grid = _dev(gpd_grid)
+    M_SG, M_NSp, M_NSm = _dev(M_SG), _dev(M_NSp), _dev(M_NSm)
+    F, nx, nxi = (int(v) for v in gpd_grid.shape[:3])
+    extra = tuple(int(v) for v in gpd_grid.shape[3:])
+    S = 1
+    for e in extra:
+        S *= e
+    nq = int(M_SG.shape[3])
+    Fout = max(F, nfl + 1)
+    out = torch.empty((Fout, nx, nxi, S, nq), dtype=torch.float64, device=gpd_grid.device)
+    if S > 0:
+        _fused_fixed_flavor(gpd_grid.reshape(F, nx, nxi, S).contiguous(), M_SG, M_NSp, M_NSm, nfl, out, 0, 0)
+    return out.reshape((Fout, nx, nxi) + extra + (nq,))
+
+
+def evolve_fixed_flavor_unfused(gpd_grid, M_SG, M_NSp, M_NSm, nfl=4):
+    ''' evolve_fixed_flavor as the reference spells it: make_evo_basis, three applications, make_flv_basis,
+    padding (reference: evolution.py:495-514). '''
     gpd_grid = _dev(gpd_grid)
     extra_nfl = gpd_grid.shape[0] - 1 - nfl
     sg_ini, t_ini, qmin_ini = make_evo_basis(gpd_grid, nfl=nfl)
