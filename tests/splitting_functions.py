@@ -123,3 +123,51 @@ def P1_gg(x, nf):
 def dP1_ps(x, nf):
     lx = np.log(x)
     return 8 * CF * TF * nf * ((1 - x) - (1 - 3 * x) * lx - (1 + x) * lx * lx)
+
+
+# ---- NLO polarised singlet, x < 1 (Mertig-van Neerven 1996, Vogelsang 1996), normalisation (alpha_s / 2 pi)^2 ----
+def _S2(x):
+    return -2 * _li2(-x) - 2 * np.log(x) * np.log(1 + x) + 0.5 * np.log(x) ** 2 - np.pi ** 2 / 6
+
+
+def _dpqg(x):
+    return 2 * x - 1
+
+
+def _dpgq(x):
+    return 2 - x
+
+
+def _dpgg(x):
+    return 1 / (1 - x) - 2 * x + 1
+
+
+def dP1_qg(x, nf):
+    lx, l1 = np.log(x), np.log(1 - x)
+    return nf * (CF * TF * (-22 + 27 * x - 9 * lx + 8 * (1 - x) * l1 + _dpqg(x) * (2 * l1 ** 2 - 4 * l1 * lx + lx ** 2 - 2 * np.pi ** 2 / 3))
+                 + CA * TF * (2 * (12 - 11 * x) - 8 * (1 - x) * l1 + 2 * (1 + 8 * x) * lx - 2 * (l1 ** 2 - np.pi ** 2 / 6) * _dpqg(x)
+                              - (2 * _S2(x) - 3 * lx ** 2) * _dpqg(-x)))
+
+
+def dP1_gq_brackets(x):
+    """(CF TF nf, CF^2, CF CA) brackets of Delta P_gq^(1); their first moments are -1/3, -9/4, 71/12
+    (Delta gamma_gq^(1)(N=1) = 18 CF^2 - 142/3 CF CA + 8/3 CF TF nf in the gamma = -8 P convention)"""
+    lx, l1 = np.log(x), np.log(1 - x)
+    b_nf = -4 / 9 * (x + 4) - 4 / 3 * _dpgq(x) * l1
+    b_ff = -0.5 - 0.5 * (4 - x) * lx - _dpgq(-x) * l1 + (-4 - l1 ** 2 + 0.5 * lx ** 2) * _dpgq(x)
+    b_fa = ((4 - 13 * x) * lx + (10 + x) / 3 * l1 + (41 + 35 * x) / 9 + 0.5 * (-2 * _S2(x) + 3 * lx ** 2) * _dpgq(-x)
+            + (l1 ** 2 - 2 * l1 * lx - np.pi ** 2 / 6) * _dpgq(x))
+    return b_nf, b_ff, b_fa
+
+
+def dP1_gq(x, nf, cf2_factor=1.0):
+    b_nf, b_ff, b_fa = dP1_gq_brackets(x)
+    return CF * TF * nf * b_nf + cf2_factor * CF ** 2 * b_ff + CF * CA * b_fa
+
+
+def dP1_gg(x, nf):
+    lx, l1 = np.log(x), np.log(1 - x)
+    return (-CA * TF * nf * (4 * (1 - x) + 4 / 3 * (1 + x) * lx + 20 / 9 * _dpgg(x))
+            - CF * TF * nf * (10 * (1 - x) + 2 * (5 - x) * lx + 2 * (1 + x) * lx ** 2)
+            + CA ** 2 * ((29 - 67 * x) / 3 * lx - 9.5 * (1 - x) + 4 * (1 + x) * lx ** 2 - 2 * _S2(x) * _dpgg(-x)
+                         + (67 / 9 - 4 * l1 * lx + lx ** 2 - np.pi ** 2 / 3) * _dpgg(x)))
