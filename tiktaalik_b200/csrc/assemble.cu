@@ -1185,7 +1185,10 @@ int launch_assemble_cst_batched(int n, int nxi, const double* xi_dev, int grid_t
 }
 // leader / follower form (assemble_cst_replay.cuh).  Streams: side[0] GG leader, side[1] NS leader,
 // side[2..6] followers (KA1_GG, KV1_GG_nfl, KA1_GG_nfl after the GG leader; KV1_NSm, KV1_NS_nfl after the NS leader).
-constexpr int RP_SLOTS = 16;             // slots per block reserved in the global list area (max over the launches)
+#ifndef TKB_RP_SLOTS
+#define TKB_RP_SLOTS 16
+#endif
+constexpr int RP_SLOTS = TKB_RP_SLOTS;             // slots per block reserved in the global list area (max over the launches)
 size_t qags_replay_lists_bytes(int nblocks) { return sizeof(QLists) * (size_t)RP_SLOTS * nblocks * 7; }
 size_t qags_replay_log_doubles(int which /*0 NS pair log, 1 unused*/, size_t ninst, int L) { return which == 0 ? ninst * (size_t)L * (4 + 42) : 0; }
 
