@@ -57,7 +57,9 @@ int tkb_get_nq2(void);
 int tkb_get_lnlo(void);
 
 /* replace evomatrix_{vns,vsg,ans,asg}_wrap (f90wrap/matrices.f90:76-110 -> matevo.f90:246-278).
- * tkb_evomatrix returns a zero-copy view (valid until the next make_kernels/make_matrices):
+ * tkb_evomatrix returns a zero-copy view (valid until the next make_kernels/make_matrices; the memory itself is
+ * only rewritten by the next tkb_make_matrices, so an asynchronous read that is already enqueued may overlap a
+ * tkb_make_kernels of the same shapes):
  * shape = (m, m, nxi, nq2) and element strides for the logical indices (i, j, xi, Q2).
  * tkb_evomatrix_copy writes a private copy in the same [xi][Q2][i][j] layout (f2py's
  * intent(out) semantics: the caller may modify it). */
