@@ -324,10 +324,8 @@ assemble_cst_pipe_kernel(int c, int n, int nxi, const double* __restrict__ xi_ar
                 const double* preS = sh.pre[s][half];
                 const double* preO = sh.pre[s][half ^ 1];
                 double out[NKERN];
-                if (seg == 1) eval_half<bit(KID), true, 1>(X, Y, Xo, Yo, out, preS, preO);
-                else if (seg == 0) eval_half<bit(KID), true, 2>(X, Y, Xo, Yo, out, preS, preO);
-                else if (seg == 3) eval_half<bit(KID), false, 1>(X, Y, Xo, Yo, out, preS, preO);
-                else eval_half<bit(KID), false, 2>(X, Y, Xo, Yo, out, preS, preO);
+                if (seg < 2) eval_half<bit(KID), true, 3>(X, Y, Xo, Yo, out, preS, preO, dir ? 2 : 1);
+                else eval_half<bit(KID), false, 3>(X, Y, Xo, Yo, out, preS, preO, dir ? 2 : 1);
                 sh.hv[s][task] = out[KID];
             }
         }

@@ -321,8 +321,11 @@ TKB_DEV double pre_value(int which, double U)
 template <unsigned MASK, bool WITH_RHO = true, int FIX = 0>
 __device__ __forceinline__ void eval_half(double X, double Y, double Xo, double Yo, double* __restrict__ out,
                                           const double* __restrict__ preS = nullptr,
-                                          const double* __restrict__ preO = nullptr)
+                                          const double* __restrict__ preO = nullptr, int fix_rt = 0)
 {
+    // FIX = 3: the side of the fixed point is a run-time (warp-uniform) argument, one copy of the formulas serves both
+    const bool F1 = (FIX == 1) || (FIX == 3 && fix_rt == 1);
+    const bool F2 = (FIX == 2) || (FIX == 3 && fix_rt == 2);
     static_assert(WITH_RHO || (MASK & ~MASK_QAGS) == 0, "erbl-only evaluation exists for the QAGS kernels only");
     constexpr bool LO_ANY = (MASK & 0x7fu) != 0;
     constexpr bool NS = (MASK & (bit(K_NSP) | bit(K_NSM))) != 0;
@@ -355,12 +358,12 @@ __device__ __forceinline__ void eval_half(double X, double Y, double Xo, double 
     if (N_lr) lr = abslog(r);
     if (N_lomr) lomr = abslog(omr);
     if (N_lyx1) { yx1 = Y / X - 1.0; lyx1 = abslog(yx1); }
-    if (N_lX) lX = (FIX == 1) ? preS[PRE_L] : abslog(X);
-    if (N_lXb) lXb = (FIX == 1) ? preS[PRE_LB] : abslog(Xb);
-    if (N_lY) lY = (FIX == 2) ? preS[PRE_L] : abslog(Y);
-    if (N_DX) DX = (FIX == 1) ? preS[PRE_D] : dilog(X);
-    if (N_DYb) DYb = (FIX == 2) ? preS[PRE_DB] : dilog(Yb);
-    if (N_DXb) DXb = (FIX == 1) ? preS[PRE_DB] : dilog(Xb);
+    if (N_lX) lX = F1 ? preS[PRE_L] : abslog(X);
+    if (N_lXb) lXb = F1 ? preS[PRE_LB] : abslog(Xb);
+    if (N_lY) lY = F2 ? preS[PRE_L] : abslog(Y);
+    if (N_DX) DX = F1 ? preS[PRE_D] : dilog(X);
+    if (N_DYb) DYb = F2 ? preS[PRE_DB] : dilog(Yb);
+    if (N_DXb) DXb = F1 ? preS[PRE_DB] : dilog(Xb);
     const double L2r = sqlog(lr, r);                      // log2(X/Y)
     const double L2X = sqlog(lX, X);                      // log2(X)
     const double LPXbY = prodlog(lXb, Xb, lY, Y);         // logprod(Xbar, Y)
@@ -370,7 +373,7 @@ __device__ __forceinline__ void eval_half(double X, double Y, double Xo, double 
     if (HV && WITH_RHO) {
         Xbb = 1.0 - Xb;
         G = 2.0 * dilog(1.0 - Xb / Y) + sqlog(lY, Y);
-        DXbb = (FIX == 1) ? preS[PRE_DBB] : dilog(Xbb);
+        DXbb = F1 ? preS[PRE_DBB] : dilog(Xbb);
     }
 
     // ---------------- LO (kernels_lo.f90:48-221) ----------------
@@ -392,7 +395,7 @@ __device__ __forceinline__ void eval_half(double X, double Y, double Xo, double 
             out[K_NSN] = WITH_RHO ? (-0.5 * CF * beta0 * (R5_3 * QQf + X / Y + QQf * lr)) * rho : 0.0;
         }
         if (NS) {
-            const double lXo = (FIX == 1) ? preO[PRE_L] : abslog(Xo);
+            const double lXo = F1 ? preO[PRE_L] : abslog(Xo);
             const double piece4 = -0.5 * X / Yo * (lX + L2X - 2.0 * prodlog(lX, X, lXo, Xo)) * (CF * CF);
             const double p4 = piece4 * erbl;
             if (!WITH_RHO) {
@@ -405,7 +408,7 @@ __device__ __forceinline__ void eval_half(double X, double Y, double Xo, double 
                 const double Xob = 1.0 - Xo;
                 const double Go = 2.0 * dilog(1.0 - Xo / Y) + sqlog(lY, Y);
                 const double QQhbar = hbar_pp(qq_fab(Xo, Y), qq_fab(Xob, Yb), Go, DYb, prodlog(lXo, Xo, lY, Y),
-                                               (FIX == 1) ? preO[PRE_DB] : dilog(Xob));
+                                               F1 ? preO[PRE_DB] : dilog(Xob));
                 const double beta0 = -R11_3 * CA;
                 const double piece1 = (CF * CF) * ((R4_3 - 2.0 * ZETA2) * QQf + 3.0 * X / Y
                     - (1.5 * QQf - 0.5 * X / Yo) * lr
