@@ -356,6 +356,23 @@ struct SpillList {                       // 1-based list, head (indices < CAP) i
     T* s;
     T* g;
     __device__ __forceinline__ T& operator[](int i) const { return (i < CAP) ? s[i] : g[i]; }
+    static constexpr int cap = CAP;
+    // entries lo .. hi move one place up (to lo+1 .. hi+1) / one place down (to lo-1 .. hi-1); the shared and the
+    // global part are walked by separate loops without the per-access select
+    __device__ __forceinline__ void shift_up(int lo, int hi) const
+    {
+        int t = hi;
+        for (; t >= lo && t >= CAP; t--) g[t + 1] = g[t];                 // source and destination in global memory
+        if (t >= lo && t == CAP - 1) { g[CAP] = s[CAP - 1]; t--; }         // the entry that crosses the boundary
+        for (; t >= lo; t--) s[t + 1] = s[t];
+    }
+    __device__ __forceinline__ void shift_down(int lo, int hi) const
+    {
+        int t = lo;
+        for (; t <= hi && t < CAP; t++) s[t - 1] = s[t];
+        if (t <= hi && t == CAP) { s[CAP - 1] = g[CAP]; t++; }
+        for (; t <= hi; t++) g[t - 1] = g[t];
+    }
 };
 using DList = SpillList<double, QCAP>;
 using IList = SpillList<int, QCAP>;
@@ -455,7 +472,7 @@ static __device__ __noinline__ void qsort_bs_(int limit, int last, int& maxerr, 
         if (errmax >= elist[iord[mid]]) hi = mid; else lo = mid + 1;
     }
     const int i = lo;
-    for (int t = ibeg; t < i; t++) iord[t - 1] = iord[t];
+    iord.shift_down(ibeg, i - 1);
     if (i > jbnd) {
         iord[jbnd] = maxerr;
         iord[jupbn] = last;
@@ -471,7 +488,7 @@ static __device__ __noinline__ void qsort_bs_(int limit, int last, int& maxerr, 
             const int mid = (klo + khi) >> 1;
             if (errmin < elist[iord[mid]]) klo = mid; else khi = mid;
         }
-        for (int t = jbnd; t > klo; t--) iord[t + 1] = iord[t];
+        iord.shift_up(klo + 1, jbnd);
         iord[klo + 1] = last;
     }
     maxerr = iord[nrmax];
