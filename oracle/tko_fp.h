@@ -179,4 +179,22 @@ static inline double tko_pow(double x, double y)
     return tko_exp_dd(ph, pl);
 }
 
+/* x**1.5 as QUADPACK's error estimate needs it (integration.f90, qk21: (200*abserr/resasc)**1.5_dp under min(1, .)).
+ * For 1e-150 < t < 1:  sqrt(t) = s + e with e from the exact residual t - s*s, so t**1.5 = t*s + t*e to ~2^-104:
+ * correctly rounded in practice, like the libm pow behind the reference (tko_pow is good to ~0.6 ulp only, and
+ * far more expensive).  t >= 1 gives a value >= 1, which min(1, .) turns into 1.  Everything else (NaN, zero,
+ * below 1e-150) goes through tko_pow. */
+static inline double tko_pow15_capped(double t)
+{
+    if (t >= 1.0) return 1.0;
+    if (t > 1e-150) {
+        double s = sqrt(t);
+        double e = fma(-s, s, t) / (2.0 * s);
+        double hi = t * s;
+        double lo = fma(t, s, -hi) + t * e;
+        return hi + lo;
+    }
+    return tko_pow(t, 1.5);
+}
+
 #endif /* TKO_FP_H */

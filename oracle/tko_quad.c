@@ -69,7 +69,7 @@ void tko_qk21(tko_f1 f, void *ctx, double a, double b,
     resasc = resasc * dhlgth;
     double err = fabs((resk - resg) * hlgth);
     if (resasc != 0.0 && err != 0.0)
-        err = resasc * tko_min(1.0, tko_pow(2.0e+02 * err / resasc, 1.5));
+        err = resasc * tko_min(1.0, tko_pow15_capped(2.0e+02 * err / resasc));
     if (resabs > TKO_TINY / (5.0e+01 * TKO_EPS))
         err = tko_max((TKO_EPS * 5.0e+01) * resabs, err);
     *abserr = err;

@@ -614,7 +614,7 @@ static __device__ __noinline__ void qk21_reduce(const double* fv, double a, doub
     resasc = resasc * dhlgth;
     abserr = fabs((resk - resg) * hlgth);
     if (resasc != 0.0 && abserr != 0.0)
-        abserr = resasc * fmin2(1.0, pow_(2.0e+02 * abserr / resasc, 1.5));
+        abserr = resasc * fmin2(1.0, pow15_capped(2.0e+02 * abserr / resasc));
     if (resabs > tiny_() / (5.0e+01 * eps_()))
         abserr = fmax2((eps_() * 5.0e+01) * resabs, abserr);
 }
