@@ -118,6 +118,30 @@ def test_all_kernel_functions_bit_identical(tk, tko, xi):
     assert ok.all(), "kernels not bit-identical: %s" % sorted(set(np.nonzero(~ok)[1].tolist()))
 
 
+def test_kernel_functions_at_singular_points(tk, tko):
+    """x = y, y = +-xi, x = +-xi, zeros and end points: the reference evaluates pieces outside their support and
+    multiplies by a vanishing step, so 0 * Inf = NaN, divisions by zero and log(0) must come out the same
+    (kernels_nlo.f90:137-141): same NaN pattern, same infinities, same finite bits"""
+    xi = 0.25
+    vals = [-1.0, -0.6, -xi, -0.1, 0.0, 0.1, xi, 0.6, 1.0, 2 * xi - 1, 1 - 2 * xi]
+    pts = [(a, b) for a in vals for b in vals]
+    x = np.array([p[0] for p in pts])
+    y = np.array([p[1] for p in pts])
+    n = len(pts)
+    L = tk._lib.lib()
+    out = torch.empty((n, 22), dtype=torch.float64, device="cuda")
+    xd, yd, xid = dev(x), dev(y), dev(np.full(n, xi))
+    tk._lib.check(L.tkb_eval_kernels(n, tk._lib.ptr(xd), tk._lib.ptr(yd), tk._lib.ptr(xid), tk._lib.ptr(out),
+                                     tk._lib.stream_ptr()))
+    torch.cuda.synchronize()
+    got = out.cpu().numpy()
+    ref = np.array([[tko.kernel(f, x[p], y[p], xi) for f in range(22)] for p in range(n)])
+    assert np.array_equal(np.isnan(got), np.isnan(ref)), "NaN pattern differs at %s" % np.argwhere(np.isnan(got) != np.isnan(ref))[:5]
+    fin = ~np.isnan(ref)
+    assert np.array_equal(got[fin], ref[fin]), np.argwhere((got != ref) & fin)[:5]
+    assert np.isnan(ref).any() and np.isinf(ref[fin]).any()          # the points do exercise the singular cases
+
+
 # --------------------------------------------------------------------------------------------
 # assembly
 
