@@ -137,6 +137,11 @@ int tkb_raw_kernel(int which, int nfl, const double** dev_ptr, void* stream);
 /* all 22 two-variable kernels at npts points: out[p][22] */
 int tkb_eval_kernels(int npts, const double* x_dev, const double* y_dev, const double* xi_dev, double* out_dev,
                      void* stream);
+/* the task skipping of the assembly kernels, exposed for the tests: for constant c (index as in tkb_qags_info) and
+ * the four half-kernel tasks of a node (K(x,y) halves 0/1, K(y,x) halves 0/1): support class (2 full, 1 erbl-only,
+ * 0 skipped as an exact zero), value of the full evaluation, value of the erbl-only evaluation; arrays [npts][4] */
+int tkb_task_classes(int c, int npts, const double* x_dev, const double* y_dev, const double* xi_dev, int* cls_dev,
+                     double* full_dev, double* erbl_dev, void* stream);
 /* which = 0 log(a), 1 pow(a,b), 2 dilog(a) with the library's own device arithmetic */
 int tkb_eval_scalar(int which, int npts, const double* a_dev, const double* b_dev, double* out_dev, void* stream);
 /* device time in ms of the stages of the last tkb_make_kernels / tkb_make_matrices:

@@ -142,6 +142,48 @@ def test_kernel_functions_at_singular_points(tk, tko):
     assert np.isnan(ref).any() and np.isinf(ref[fin]).any()          # the points do exercise the singular cases
 
 
+@pytest.mark.parametrize("c", range(7))
+def test_skipped_tasks_are_exact_zeros_and_erbl_only_tasks_lose_nothing(tk, c):
+    """The assembly kernels skip half kernels of class 0 and evaluate only the ERBL pieces of class 1.  On random,
+    near-singular (a few ulps from x = y, y = +-xi, 0, +-1) and exactly singular nodes: class 0 => the full evaluation
+    is an exact zero, class 1 => the erbl-only evaluation equals the full one bit for bit (NaN for NaN)."""
+    rng = np.random.default_rng(100 + c)
+    pts = []
+    for xi in (0.5, 0.05, 1e-3, 2e-5):
+        n = 1500
+        x = rng.uniform(-1, 1, n)
+        y = rng.uniform(-1, 1, n)
+        x[: n // 3] = rng.uniform(-1.5, 1.5, n // 3) * xi
+        y[n // 6: n // 2] = rng.uniform(-1.5, 1.5, n // 2 - n // 6) * xi
+        special = np.array([0.0, xi, -xi, 1.0, -1.0, 0.3, -0.3, 2 * xi, 1 - 2 * xi if xi < 0.5 else 0.1])
+        near = np.concatenate([np.nextafter(special, 2.0), np.nextafter(special, -2.0), special,
+                               special * (1 + 4e-16), special * (1 - 4e-16)])
+        xs = np.concatenate([x, rng.choice(near, 600), rng.choice(near, 600), rng.uniform(-1, 1, 300)])
+        ys = np.concatenate([y, rng.choice(near, 600), rng.uniform(-1, 1, 600), rng.choice(near, 300)])
+        # y a few ulps from x as well
+        xs = np.concatenate([xs, x[:300]])
+        ys = np.concatenate([ys, np.nextafter(x[:300], rng.choice([-2.0, 2.0], 300))])
+        pts.append((xs, ys, np.full(xs.shape[0], xi)))
+    x = np.concatenate([p[0] for p in pts]); y = np.concatenate([p[1] for p in pts]); xi = np.concatenate([p[2] for p in pts])
+    n = x.shape[0]
+    L = tk._lib.lib()
+    cls = torch.empty((n, 4), dtype=torch.int32, device="cuda")
+    full = torch.empty((n, 4), dtype=torch.float64, device="cuda")
+    erbl = torch.empty((n, 4), dtype=torch.float64, device="cuda")
+    xd, yd, xid = dev(x), dev(y), dev(xi)
+    tk._lib.check(L.tkb_task_classes(c, n, tk._lib.ptr(xd), tk._lib.ptr(yd), tk._lib.ptr(xid), tk._lib.ptr(cls),
+                                     tk._lib.ptr(full), tk._lib.ptr(erbl), tk._lib.stream_ptr()))
+    torch.cuda.synchronize()
+    cls, full, erbl = cls.cpu().numpy(), full.cpu().numpy(), erbl.cpu().numpy()
+    dead = cls == 0
+    assert np.all(full[dead] == 0.0), "a skipped task is not an exact zero: %s" % np.argwhere(dead & (full != 0.0))[:5]
+    one = cls == 1
+    same = (bits(full) == bits(erbl)) | (np.isnan(full) & np.isnan(erbl)) | ((full == 0) & (erbl == 0))
+    assert np.all(same[one]), "erbl-only evaluation differs: %s" % np.argwhere(one & ~same)[:5]
+    assert dead.sum() > 1000 and one.sum() > 100 and (cls == 2).sum() > 1000       # all classes are exercised
+    assert np.isnan(full).any()                                                     # and so are the singular nodes
+
+
 # --------------------------------------------------------------------------------------------
 # assembly
 

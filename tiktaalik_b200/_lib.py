@@ -42,6 +42,7 @@ SIGNATURES = {
     "tkb_stage_ms": (C.c_int, [_dp]),
     "tkb_launch_count": (C.c_longlong, []),
     "tkb_set_variant": (C.c_int, [C.c_int, C.c_int]),
+    "tkb_task_classes": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "tkb_evolve_workspace": (C.c_int64, [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int]),
     "tkb_evolve_fixed_flavor": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, _dp, _dp,
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,

@@ -1093,6 +1093,54 @@ __global__ void eval_scalar_kernel(int which, int npts, const double* __restrict
     }
 }
 
+// test hook for the task skipping of K1 / K2: per point and for the four half-kernel tasks of a node
+// (K(x,y) halves 0/1, K(y,x) halves 0/1): the support class the assembly kernels would assign, the value of the
+// full evaluation and the value of the erbl-only evaluation of one QAGS kernel.  The tests require: class 0 =>
+// the full value is an exact zero; class 1 => the erbl-only value equals the full value bit for bit.
+template <int KID>
+__global__ void task_classes_kernel(int npts, const double* __restrict__ xs, const double* __restrict__ ys,
+                                    const double* __restrict__ xis, int* __restrict__ cls /*[npts][4]*/,
+                                    double* __restrict__ full /*[npts][4]*/, double* __restrict__ erbl /*[npts][4]*/)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npts) return;
+    const double x = xs[p], y = ys[p], xi = xis[p];
+    const double xx1 = 0.5 * (1.0 + x / xi), xx2 = 0.5 * (1.0 - x / xi);
+    const double yy1 = 0.5 * (1.0 + y / xi), yy2 = 0.5 * (1.0 - y / xi);
+    const bool safe = node_is_safe(xx1, xx2, yy1, yy2);
+    for (int k = 0; k < 4; k++) {
+        const int dir = k >> 1, half = k & 1;
+        const double U1 = dir ? yy1 : xx1, U2 = dir ? yy2 : xx2, V1 = dir ? xx1 : yy1, V2 = dir ? xx2 : yy2;
+        const double X = half ? U2 : U1, Y = half ? V2 : V1, Xo = half ? U1 : U2, Yo = half ? V1 : V2;
+        double out[NKERN];
+        cls[4 * p + k] = task_class(X, Y, safe);
+        eval_half<bit(KID), true>(X, Y, Xo, Yo, out);
+        full[4 * p + k] = out[KID];
+        eval_half<bit(KID), false>(X, Y, Xo, Yo, out);
+        erbl[4 * p + k] = out[KID];
+    }
+}
+
+int launch_task_classes(int c, int npts, const double* xs, const double* ys, const double* xis, int* cls, double* full,
+                        double* erbl, cudaStream_t st)
+{
+    const int g = (npts + 63) / 64;
+    switch (c) {
+    case 0: task_classes_kernel<K_NSP><<<g, 64, 0, st>>>(npts, xs, ys, xis, cls, full, erbl); break;
+    case 1: task_classes_kernel<K_NSM><<<g, 64, 0, st>>>(npts, xs, ys, xis, cls, full, erbl); break;
+    case 2: task_classes_kernel<K_NSN><<<g, 64, 0, st>>>(npts, xs, ys, xis, cls, full, erbl); break;
+    case 3: task_classes_kernel<K_V1GG><<<g, 64, 0, st>>>(npts, xs, ys, xis, cls, full, erbl); break;
+    case 4: task_classes_kernel<K_A1GG><<<g, 64, 0, st>>>(npts, xs, ys, xis, cls, full, erbl); break;
+    case 5: task_classes_kernel<K_V1GGN><<<g, 64, 0, st>>>(npts, xs, ys, xis, cls, full, erbl); break;
+    case 6: task_classes_kernel<K_A1GGN><<<g, 64, 0, st>>>(npts, xs, ys, xis, cls, full, erbl); break;
+    default: return set_error("tkb_task_classes: constant index out of range");
+    }
+    ++g_launches;
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
+    return 0;
+}
+
 // ---------------------------------------------------------------------------------------
 // host launchers
 

@@ -554,6 +554,14 @@ int tkb_eval_scalar(int which, int npts, const double* a_dev, const double* b_de
     return launch_eval_scalar(which, npts, a_dev, b_dev, out_dev, (cudaStream_t)stream);
 }
 
+int tkb_task_classes(int c, int npts, const double* x_dev, const double* y_dev, const double* xi_dev, int* cls_dev,
+                     double* full_dev, double* erbl_dev, void* stream)
+{
+    if (npts < 0 || !x_dev || !y_dev || !xi_dev || !cls_dev || !full_dev || !erbl_dev) return set_error("tkb_task_classes: bad arguments");
+    if (npts == 0) return 0;
+    return launch_task_classes(c, npts, x_dev, y_dev, xi_dev, cls_dev, full_dev, erbl_dev, (cudaStream_t)stream);
+}
+
 int tkb_stage_ms(double ms[3])
 {
     ms[0] = ms[1] = ms[2] = 0.0;

@@ -35,6 +35,8 @@ int qags_batched_blocks_per_sm();
 int launch_compose(int n, int nxi, int nfl, const double* P, const double* diag, const double* cst_res,
                    double* NS0, double* NS1p, double* NS1m, double* SGV0, double* SGA0, double* SGV1, double* SGA1,
                    cudaStream_t st);
+int launch_task_classes(int c, int npts, const double* xs, const double* ys, const double* xis, int* cls, double* full,
+                        double* erbl, cudaStream_t st);
 int launch_eval_kernels(int npts, const double* xs, const double* ys, const double* xis, double* out, cudaStream_t st);
 int launch_eval_scalar(int which, int npts, const double* a, const double* b, double* out, cudaStream_t st);
 
