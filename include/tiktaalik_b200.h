@@ -139,7 +139,9 @@ int tkb_eval_kernels(int npts, const double* x_dev, const double* y_dev, const d
                      void* stream);
 /* the task skipping of the assembly kernels, exposed for the tests: for constant c (index as in tkb_qags_info) and
  * the four half-kernel tasks of a node (K(x,y) halves 0/1, K(y,x) halves 0/1): support class (2 full, 1 erbl-only,
- * 0 skipped as an exact zero), value of the full evaluation, value of the erbl-only evaluation; arrays [npts][4] */
+ * 0 skipped as an exact zero), value of the full evaluation, value of the erbl-only evaluation; arrays [npts][4].
+ * c = 7: all 22 kernels at once as the fixed-quadrature kernel evaluates them; full = number of values that are not
+ * an exact zero */
 int tkb_task_classes(int c, int npts, const double* x_dev, const double* y_dev, const double* xi_dev, int* cls_dev,
                      double* full_dev, double* erbl_dev, void* stream);
 /* which = 0 log(a), 1 pow(a,b), 2 dilog(a) with the library's own device arithmetic */

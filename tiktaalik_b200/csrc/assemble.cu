@@ -1121,6 +1121,32 @@ __global__ void task_classes_kernel(int npts, const double* __restrict__ xs, con
     }
 }
 
+// the same for K1, which skips class-0 halves for all 22 kernels at once: full[.] = number of the 22 half-kernel
+// values that are not an exact zero (NaN counts), erbl[.] = 0
+__global__ void task_classes_all_kernel(int npts, const double* __restrict__ xs, const double* __restrict__ ys,
+                                        const double* __restrict__ xis, int* __restrict__ cls,
+                                        double* __restrict__ full, double* __restrict__ erbl)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npts) return;
+    const double x = xs[p], y = ys[p], xi = xis[p];
+    const double xx1 = 0.5 * (1.0 + x / xi), xx2 = 0.5 * (1.0 - x / xi);
+    const double yy1 = 0.5 * (1.0 + y / xi), yy2 = 0.5 * (1.0 - y / xi);
+    const bool safe = node_is_safe(xx1, xx2, yy1, yy2);
+    for (int k = 0; k < 4; k++) {
+        const int dir = k >> 1, half = k & 1;
+        const double U1 = dir ? yy1 : xx1, U2 = dir ? yy2 : xx2, V1 = dir ? xx1 : yy1, V2 = dir ? xx2 : yy2;
+        const double X = half ? U2 : U1, Y = half ? V2 : V1, Xo = half ? U1 : U2, Yo = half ? V1 : V2;
+        double out[NKERN];
+        cls[4 * p + k] = task_class(X, Y, safe);
+        eval_half<MASK_ALL, true>(X, Y, Xo, Yo, out);
+        int nz = 0;
+        for (int f = 0; f < NKERN; f++) nz += !(out[f] == 0.0);
+        full[4 * p + k] = (double)nz;
+        erbl[4 * p + k] = 0.0;
+    }
+}
+
 int launch_task_classes(int c, int npts, const double* xs, const double* ys, const double* xis, int* cls, double* full,
                         double* erbl, cudaStream_t st)
 {
@@ -1133,6 +1159,7 @@ int launch_task_classes(int c, int npts, const double* xs, const double* ys, con
     case 4: task_classes_kernel<K_A1GG><<<g, 64, 0, st>>>(npts, xs, ys, xis, cls, full, erbl); break;
     case 5: task_classes_kernel<K_V1GGN><<<g, 64, 0, st>>>(npts, xs, ys, xis, cls, full, erbl); break;
     case 6: task_classes_kernel<K_A1GGN><<<g, 64, 0, st>>>(npts, xs, ys, xis, cls, full, erbl); break;
+    case 7: task_classes_all_kernel<<<g, 64, 0, st>>>(npts, xs, ys, xis, cls, full, erbl); break;
     default: return set_error("tkb_task_classes: constant index out of range");
     }
     ++g_launches;
