@@ -7,11 +7,11 @@
 //     M   [xi][Q2][i][j]   row-major m x m tiles (what make_matrices produces)
 //     g   [j][xi][s]       the caller's (m, nxi, S) C-contiguous array, consumed in place
 //     out [xi][Q2][i][s]   returned to Python as a permuted view of shape (m, nxi, S, nQ2)
-// Two regimes: small S is HBM-bound on reading M (0.25..1.9 flop/B) and uses a
-// warp-per-row kernel with 16-byte coalesced loads (S <= 4 by default; the kernel exists up to 8,
-// TKB_APPLY_SMALL_MAX); larger S uses the batched FP64 tensor-core GEMM of rk4.cu with a tile as
-// narrow as the sample count and the right-hand side shared by the nQ2 matrices of one xi
-// (HBM-bound up to S ~ 24, FP64-bound beyond).
+// Two regimes: HBM-bound on reading M up to S ~ 24 (0.25..6 flop/B), FP64-bound beyond.  Both run
+// the batched FP64 tensor-core GEMM of rk4.cu (cp.async, three stages) with a tile as narrow as the sample count
+// (16 columns up to S = 16, so M is streamed exactly once) and the right-hand side shared by the nQ2 matrices of
+// one xi.  The warp-per-row kernel below (S <= 8) was the first small-S path; it is kept behind
+// TKB_APPLY_SMALL_MAX and serves matrices with fewer than 40 rows.
 #include <cstdlib>
 #include <cuda_runtime.h>
 #include "tkb_internal.h"
@@ -86,8 +86,8 @@ int launch_apply(int m, int nxi, int nq2, int64_t S, const double* M, const doub
 {
     if (S <= 0) return 0;
     const int nb = nxi * nq2;
-    static const int small_max = [] { const char* e = getenv("TKB_APPLY_SMALL_MAX"); const int v = e ? atoi(e) : 4;   /* measured: from S = 5 the narrow-tile DMMA GEMM is faster */ return v < 0 ? 0 : (v > GEMV_MAXS ? GEMV_MAXS : v); }();
-    if (S <= small_max && (m % 2) == 0 && (size_t)m * S * sizeof(double) <= 48 * 1024) {
+    static const int small_max = [] { const char* e = getenv("TKB_APPLY_SMALL_MAX"); const int v = e ? atoi(e) : 0;   /* measured: the cp.async DMMA GEMM with a 16-column tile is faster for every S */ return v < 0 ? 0 : (v > GEMV_MAXS ? GEMV_MAXS : v); }();
+    if ((S <= small_max || (m < 40 && S <= GEMV_MAXS)) && (m % 2) == 0 && (size_t)m * S * sizeof(double) <= 48 * 1024) {
         switch ((int)S) {
         case 1: return launch_small<1>(m, nb, nq2, M, g, ldg, out, st);
         case 2: return launch_small<2>(m, nb, nq2, M, g, ldg, out, st);

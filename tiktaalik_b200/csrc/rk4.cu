@@ -24,6 +24,7 @@ namespace tkb {
 
 constexpr int GEMM_BK = 16;
 static const bool g_gemm_no_dmma = (getenv("TKB_GEMM_DFMA") != nullptr);     // comparison knob: DFMA kernels only
+static const bool g_gemm_sync = (getenv("TKB_GEMM_SYNC") != nullptr);        // comparison knob: register-staged DMMA kernel
 
 // C = D + alpha * A B.  Block tile (16 T) x (16 T); thread (ty, tx) owns rows ty + 16 a, cols tx + 16 b.
 // Two shared-memory stages: the global loads of tile k+1 are issued into registers before the
@@ -248,6 +249,140 @@ gemm_dmma_kernel(int M, int N, int K, double alpha,
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// The same MMA tiling fed by cp.async: operand tiles go from global to shared memory without passing through
+// registers, three stages deep, so that a block keeps two 16-wide k-steps of HBM traffic in flight while it
+// computes on the third (the register-staged kernel above has one).  A is kept row-major in shared memory,
+// As[m][k] with a row stride of 20 doubles: a 16-lane half warp reads a[row = lane/4][k = lane%4] at
+// 20 (lane/4) + lane%4 = distinct residues mod 16, i.e. conflict-free, and a 16-byte cp.async chunk is two
+// consecutive k of one row.  B rows are copied with 8-byte chunks (their leading dimension may be odd).
+constexpr int DA_STAGES = 3;
+constexpr int DA_LDA = GEMM_BK + 4;
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes)
+{
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sa), "l"(gmem), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem, int src_bytes)
+{
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(sa), "l"(gmem), "r"(src_bytes) : "memory");
+}
+
+template <int NJ>
+__global__ void __launch_bounds__(128)
+gemm_dmma_async_kernel(int M, int N, int K, double alpha,
+                       const double* __restrict__ A, int lda, int64_t strideA,
+                       const double* __restrict__ B, int ldb, int64_t strideB, int bdivB,
+                       const double* __restrict__ D, int ldd, int64_t strideD,
+                       double* __restrict__ C, int ldc, int64_t strideC)
+{
+    constexpr int BN = 16 * NJ, LDB = BN + DM_PAD;
+    extern __shared__ __align__(16) double dsm[];
+    double (*As)[DM_BT][DA_LDA] = reinterpret_cast<double (*)[DM_BT][DA_LDA]>(dsm);                       // [stage][m][k]
+    double (*Bs)[GEMM_BK][LDB] = reinterpret_cast<double (*)[GEMM_BK][LDB]>(dsm + DA_STAGES * DM_BT * DA_LDA);   // [stage][k][n]
+    const int b = blockIdx.z;
+    A += (int64_t)b * strideA;
+    B += (int64_t)(b / bdivB) * strideB;
+    C += (int64_t)b * strideC;
+    if (D) D += (int64_t)b * strideD;
+    const int row0 = blockIdx.y * DM_BT, col0 = blockIdx.x * BN;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int wr = (warp >> 1) * DM_WT, wc = (warp & 1) * (8 * NJ);
+    const int fr = lane >> 2, fk = lane & 3;
+
+    double acc[DM_NT][NJ][2];
+#pragma unroll
+    for (int i = 0; i < DM_NT; i++)
+#pragma unroll
+        for (int j = 0; j < NJ; j++) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+
+    auto issue_tile = [&](int k0, int st) {
+        // A: 80 rows x 8 chunks of 2 doubles
+#pragma unroll
+        for (int u = 0; u < (DM_BT * GEMM_BK / 2) / 128; u++) {
+            const int e = tid + 128 * u;
+            const int r = e >> 3, ch = e & 7;
+            const int gr = row0 + r, gk = k0 + 2 * ch;
+            const bool ok = (gr < M) && (gk < K);                        // K is even: a chunk is inside or outside
+            cp_async16(&As[st][r][2 * ch], ok ? (const void*)(A + (int64_t)gr * lda + gk) : (const void*)A, ok ? 16 : 0);
+        }
+        // B: 16 rows x BN doubles
+#pragma unroll
+        for (int u = 0; u < (GEMM_BK * BN) / 128; u++) {
+            const int e = tid + 128 * u;
+            const int kk = e / BN, c = e - kk * BN;
+            const int gk = k0 + kk, gc = col0 + c;
+            const bool ok = (gk < K) && (gc < N);
+            cp_async8(&Bs[st][kk][c], ok ? (const void*)(B + (int64_t)gk * ldb + gc) : (const void*)B, ok ? 8 : 0);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    const int nk = (K + GEMM_BK - 1) / GEMM_BK;
+#pragma unroll
+    for (int p = 0; p < DA_STAGES - 1; p++) {
+        if (p < nk) issue_tile(p * GEMM_BK, p);
+        else asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    for (int kt = 0; kt < nk; kt++) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(DA_STAGES - 2) : "memory");
+        __syncthreads();
+        {
+            const int nxt = kt + DA_STAGES - 1;
+            if (nxt < nk) issue_tile(nxt * GEMM_BK, nxt % DA_STAGES);
+            else asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+        const int st = kt % DA_STAGES;
+#pragma unroll
+        for (int k4 = 0; k4 < GEMM_BK; k4 += 4) {
+            double af[DM_NT], bf[NJ];
+#pragma unroll
+            for (int i = 0; i < DM_NT; i++) af[i] = As[st][wr + 8 * i + fr][k4 + fk];
+#pragma unroll
+            for (int j = 0; j < NJ; j++) bf[j] = Bs[st][k4 + fk][wc + 8 * j + fr];
+#pragma unroll
+            for (int i = 0; i < DM_NT; i++)
+#pragma unroll
+                for (int j = 0; j < NJ; j++) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < DM_NT; i++) {
+        const int gr = row0 + wr + 8 * i + fr;
+        if (gr >= M) continue;
+#pragma unroll
+        for (int j = 0; j < NJ; j++) {
+            const int gc = col0 + wc + 8 * j + 2 * fk;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                if (gc + h >= N) continue;
+                double v = alpha * acc[i][j][h];
+                if (D) v = D[(int64_t)gr * ldd + gc + h] + v;
+                C[(int64_t)gr * ldc + gc + h] = v;
+            }
+        }
+    }
+}
+
+template <int NJ>
+static cudaError_t launch_dmma_async(dim3 grid, cudaStream_t st, int M, int N, int K, double alpha, const double* A, int lda,
+                                     int64_t strideA, const double* B, int ldb, int64_t strideB, int bdivB, const double* D,
+                                     int ldd, int64_t strideD, double* C, int ldc, int64_t strideC)
+{
+    const size_t smem = sizeof(double) * DA_STAGES * (DM_BT * DA_LDA + GEMM_BK * (16 * NJ + DM_PAD));
+    static bool attr_done = false;
+    if (!attr_done) {
+        const cudaError_t e = cudaFuncSetAttribute(gemm_dmma_async_kernel<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    gemm_dmma_async_kernel<NJ><<<grid, 128, smem, st>>>(M, N, K, alpha, A, lda, strideA, B, ldb, strideB, bdivB, D, ldd, strideD,
+                                                        C, ldc, strideC);
+    return cudaGetLastError();
+}
+
 int launch_gemm(int M, int N, int K, double alpha,
                 const double* A, int lda, int64_t strideA,
                 const double* B, int ldb, int64_t strideB, int bdivB,
@@ -266,16 +401,24 @@ int launch_gemm(int M, int N, int K, double alpha,
         const double* Bb = B + (int64_t)(b0 / bdivB) * strideB;
         const double* Db = D ? D + (int64_t)b0 * strideD : nullptr;
         double* Cb = C + (int64_t)b0 * strideC;
+        // cp.async path: 16-byte chunks of A need even K, lda, strideA and an aligned base
+        const bool async_ok = !g_gemm_sync && (K % 2 == 0) && (lda % 2 == 0) && (strideA % 2 == 0) &&
+                              (((uintptr_t)Ab & 15) == 0) && (((uintptr_t)Bb & 7) == 0);
 #define TKB_DMMA(NJ)                                                                                                  \
     {                                                                                                                 \
         dim3 grid((N + 16 * NJ - 1) / (16 * NJ), (M + DM_BT - 1) / DM_BT, nb);                                        \
-        gemm_dmma_kernel<NJ><<<grid, 128, 0, st>>>(M, N, K, alpha, Ab, lda, strideA, Bb, ldb, strideB, bdivB, Db, ldd, \
-                                                   strideD, Cb, ldc, strideC);                                        \
+        if (async_ok) {                                                                                               \
+            const cudaError_t e_ = launch_dmma_async<NJ>(grid, st, M, N, K, alpha, Ab, lda, strideA, Bb, ldb, strideB, bdivB, \
+                                                         Db, ldd, strideD, Cb, ldc, strideC);                         \
+            if (e_ != cudaSuccess) return set_error(cudaGetErrorString(e_));                                           \
+        } else                                                                                                        \
+            gemm_dmma_kernel<NJ><<<grid, 128, 0, st>>>(M, N, K, alpha, Ab, lda, strideA, Bb, ldb, strideB, bdivB, Db, ldd, \
+                                                       strideD, Cb, ldc, strideC);                                    \
     }
         // tile width 16 NJ: the one that wastes the least time on padding columns; measured throughput of a full
         // tile on B200 (TFLOP/s at N = 16 NJ, m = 320): 14.3, 22.7, 25.6, 27.7, 24.2
         int best = 0;
-        if (N > 4 && M >= 40 && !g_gemm_no_dmma) {
+        if (N >= 1 && M >= 40 && !g_gemm_no_dmma) {
             const double eff[5] = { 14.3, 22.7, 25.6, 27.7, 24.2 };
             double cost = 0.0;
             for (int nj = 1; nj <= 5; nj++) {
