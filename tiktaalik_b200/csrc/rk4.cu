@@ -416,10 +416,10 @@ int launch_gemm(int M, int N, int K, double alpha,
                                                        strideD, Cb, ldc, strideC);                                    \
     }
         // tile width 16 NJ: the one that wastes the least time on padding columns; measured throughput of a full
-        // tile on B200 (TFLOP/s at N = 16 NJ, m = 320): 14.3, 22.7, 25.6, 27.7, 24.2
+        // tile on B200 (TFLOP/s at N = 16 NJ, m = 320, cp.async kernel): 22.3, 30.1, 30.8, 30.8, 30.1
         int best = 0;
         if (N >= 1 && M >= 40 && !g_gemm_no_dmma) {
-            const double eff[5] = { 14.3, 22.7, 25.6, 27.7, 24.2 };
+            const double eff[5] = { 22.3, 30.1, 30.8, 30.8, 30.1 };
             double cost = 0.0;
             for (int nj = 1; nj <= 5; nj++) {
                 const int w = 16 * nj;
