@@ -87,8 +87,10 @@ int tkb_apply(int m, int nxi, int nq2, int64_t S, const double* M_dev, const dou
  * flavours nfl, fused: one decoupling kernel, three applications, one recoupling kernel.
  *   gpd_dev  [F][nx][nxi][S]       flavour basis, row 0 gluon, rows 1.. quarks (u, d, s, ...); missing rows count as zero
  *   M_*_dev  [xi][Q2][m][m]        the segment's singlet (m = 2 nx), plus-type and minus-type non-singlet matrices
- *   out_dev  [Fout][nx][nxi][S][ldq]  receives the nq2 - skip last Q2 points of the segment in columns q0, q0 + 1, ...
- *                                  (skip = 1 drops the segment's first point, which repeats its input); rows > nfl are zero
+ *   out_dev  [Fout][nx][nxi][ldq][S]  receives the nq2 - skip last Q2 points of the segment in Q2 rows q0, q0 + 1, ...
+ *                                  (skip = 1 drops the segment's first point, which repeats its input); flavour rows
+ *                                  > nfl are zero.  The sample index is the fastest one (coalesced on both sides);
+ *                                  the Python layer returns the permuted view (flavour, x, xi, sample, Q2)
  *   tpls_host, tpls_inv_host       the nfl x nfl matrix (u+, d+, ...) -> (Sigma, T3, T8, ...) of evolution.py:517-529 and its
  *                                  inverse (np.linalg.inv in the reference), row-major, host memory
  *   work_dev                       tkb_evolve_workspace(...) doubles of device scratch */

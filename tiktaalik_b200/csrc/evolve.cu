@@ -4,7 +4,7 @@
 // np.einsum('ijkl,jk...->ik...l') applications (:507-509) -> make_flv_basis (:465-492) -> zero padding
 // (:532-540), about a dozen full-size numpy temporaries per threshold segment.  Here: one decoupling
 // kernel, the three applications (apply.cu), one recoupling kernel that writes straight into the caller's
-// (flavour, x, xi, sample, Q2) array at the segment's Q2 columns.
+// [flavour][x][xi][Q2][sample] array at the segment's Q2 rows.
 //
 //   decouple:  q_f(x) -+ q_f(-x) for the nfl active quark rows (the x grid is symmetric: -x_j = x_{n-1-j}),
 //              (Sigma, T3, T8, ...) = Tpls (q - qflip), the singlet stacked on the gluon row;
@@ -56,62 +56,43 @@ __global__ void evolve_decouple_kernel(int n, int nxi, int64_t S, int nfl, int F
 }
 
 // sg_out [xi][Q][2n][S], t_out [xi][Q][n][(nfl-1) S], qm_out [xi][Q][n][nfl S]
-//   -> out[f][i][xi][s][q0 + q - skip], q = skip .. nq-1, f = 0 .. Fout-1; out has ldq Q2 columns.
-// The applications leave Q2 slow and the sample index fast, the result wants Q2 fastest: one block transposes a
-// tile of 32 samples x 16 Q2 points of one (xi, i) through shared memory, so that both the reads (along s) and
-// the writes (along Q2) are coalesced.
-constexpr int RC_TS = 32, RC_TQ = 16;
+//   -> out[f][i][xi][q0 + q - skip][s], q = skip .. nq-1, f = 0 .. Fout-1; out has ldq Q2 rows per (f, i, xi).
+// The sample index stays the fastest one on both sides, so reads and writes are fully coalesced; the host layer
+// hands the result out as a permuted view of logical shape (flavour, x, xi, sample, Q2).
 __global__ void __launch_bounds__(256)
 evolve_recouple_kernel(int n, int nxi, int nq, int64_t S, int nfl, int Fout, FlavourRot R,
                        const double* __restrict__ sg_out, const double* __restrict__ t_out,
                        const double* __restrict__ qm_out, double* __restrict__ out, int64_t ldq, int q0, int skip)
 {
-    __shared__ double tile[6][RC_TS][RC_TQ + 1];
     const int nqk = nq - skip;
-    const int nqt = (nqk + RC_TQ - 1) / RC_TQ;
-    const int64_t nst = (S + RC_TS - 1) / RC_TS;
-    int64_t bid = blockIdx.x;
-    const int qt = (int)(bid % nqt); bid /= nqt;
-    const int64_t stile = bid % nst; bid /= nst;
-    const int64_t i = bid % n;
-    const int64_t k = bid / n;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;             // 32 x 8
-    const int64_t s = stile * RC_TS + tx;
-    for (int ql = ty; ql < RC_TQ; ql += 8) {
-        const int qq = qt * RC_TQ + ql;
-        if (s < S && qq < nqk) {
-            const int64_t bm = k * nq + (qq + skip);                     // (xi, Q2) matrix index
-            double st[5];
-            st[0] = sg_out[(bm * 2 * n + i) * S + s];
+    const int64_t total = (int64_t)nxi * n * nqk * S;
+    const int64_t fstride = (int64_t)n * nxi * ldq * S;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t s = e % S;
+        int64_t r = e / S;
+        const int qq = (int)(r % nqk); r /= nqk;
+        const int64_t i = r % n;
+        const int64_t k = r / n;
+        const int64_t bm = k * nq + (qq + skip);                         // (xi, Q2) matrix index
+        double st[5];
+        st[0] = sg_out[(bm * 2 * n + i) * S + s];
 #pragma unroll
-            for (int f = 1; f < 5; f++)
-                st[f] = (f < nfl) ? t_out[(bm * n + i) * ((int64_t)(nfl - 1) * S) + (int64_t)(f - 1) * S + s] : 0.0;
-            tile[0][tx][ql] = sg_out[(bm * 2 * n + n + i) * S + s];      // gluon
+        for (int f = 1; f < 5; f++)
+            st[f] = (f < nfl) ? t_out[(bm * n + i) * ((int64_t)(nfl - 1) * S) + (int64_t)(f - 1) * S + s] : 0.0;
+        const int64_t obase = (((i * nxi + k) * ldq) + (q0 + qq)) * S + s;
+        out[obase] = sg_out[(bm * 2 * n + n + i) * S + s];               // gluon
 #pragma unroll
-            for (int f = 0; f < 5; f++) {
-                double v = 0.0;
-                if (f < nfl) {
-                    double qp = 0.0;
+        for (int f = 0; f < 5; f++) {
+            if (f < nfl) {
+                double qp = 0.0;
 #pragma unroll
-                    for (int m = 0; m < 5; m++)
-                        if (m < nfl) qp = qp + R.N[f * nfl + m] * st[m];
-                    const double qm = qm_out[(bm * n + i) * ((int64_t)nfl * S) + (int64_t)f * S + s];
-                    v = (qp + qm) / 2.0;
-                }
-                tile[f + 1][tx][ql] = v;
+                for (int m = 0; m < 5; m++)
+                    if (m < nfl) qp = qp + R.N[f * nfl + m] * st[m];
+                const double qm = qm_out[(bm * n + i) * ((int64_t)nfl * S) + (int64_t)f * S + s];
+                out[(int64_t)(f + 1) * fstride + obase] = (qp + qm) / 2.0;
             }
         }
-    }
-    __syncthreads();
-    const int64_t fstride = (int64_t)n * nxi * S * ldq;
-    for (int t = threadIdx.x; t < RC_TS * RC_TQ; t += 256) {
-        const int sl = t / RC_TQ, ql = t - sl * RC_TQ;
-        const int64_t ss = stile * RC_TS + sl;
-        const int qq = qt * RC_TQ + ql;
-        if (ss < S && qq < nqk) {
-            const int64_t obase = ((i * nxi + k) * S + ss) * ldq + (q0 + qq);
-            for (int f = 0; f < Fout; f++) out[(int64_t)f * fstride + obase] = tile[f][sl][ql];
-        }
+        for (int f = nfl + 1; f < Fout; f++) out[(int64_t)f * fstride + obase] = 0.0;
     }
 }
 
@@ -150,12 +131,8 @@ int launch_evolve_fixed_flavor(int n, int nxi, int nq, int64_t S, int nfl, int F
     if (launch_apply(2 * n, nxi, nq, S, M_sg, sg_in, (int64_t)nxi * S, sg_out, st)) return 1;
     if (nfl > 1 && launch_apply(n, nxi, nq, (int64_t)(nfl - 1) * S, M_nsp, t_in, (int64_t)nxi * (nfl - 1) * S, t_out, st)) return 1;
     if (launch_apply(n, nxi, nq, (int64_t)nfl * S, M_nsm, qm_in, (int64_t)nxi * nfl * S, qm_out, st)) return 1;
-    {
-        const int64_t nblk = (int64_t)nxi * n * ((S + RC_TS - 1) / RC_TS) * ((nq - skip + RC_TQ - 1) / RC_TQ);
-        if (nblk > 0x7fffffffLL) return set_error("tkb_evolve_fixed_flavor: too many samples for one call; tile over samples");
-        evolve_recouple_kernel<<<(unsigned)nblk, 256, 0, st>>>(n, nxi, nq, S, nfl, Fout, R, sg_out, t_out, qm_out, out, ldq,
-                                                               q0, skip);
-    }
+    evolve_recouple_kernel<<<ew_grid((int64_t)u * (nq - skip)), 256, 0, st>>>(n, nxi, nq, S, nfl, Fout, R, sg_out, t_out,
+                                                                           qm_out, out, ldq, q0, skip);
     ++g_launches;
     e = cudaGetLastError();
     if (e != cudaSuccess) return set_error(cudaGetErrorString(e));

@@ -145,18 +145,19 @@ class Evolver:
             S *= e
         Fout = max(F, self.nfl + 1)
         nq_tot = 1 + sum(int(t[0].shape[3]) - 1 for t in trip)
-        out = torch.empty((Fout, nx, nxi, S, nq_tot), dtype=torch.float64, device=gpd_grid.device)
+        # stored [flavour][x][xi][Q2][sample] (sample fastest: coalesced in the kernels), returned as a permuted view
+        out = torch.empty((Fout, nx, nxi, nq_tot, S), dtype=torch.float64, device=gpd_grid.device)
         cur = torch.zeros((Fout, nx, nxi, S), dtype=torch.float64, device=gpd_grid.device)
         cur[:F] = gpd_grid.reshape(F, nx, nxi, S)
-        out[..., 0] = cur
+        out[:, :, :, 0, :] = cur
         q0 = 1
         for (seg, nfl), (M_SG, M_NSp, M_NSm) in zip(segs, trip):
             nq = int(M_SG.shape[3])
             if S > 0 and nq > 1:
                 _fused_fixed_flavor(cur, M_SG, M_NSp, M_NSm, nfl, out, q0, 1)
             q0 += nq - 1
-            cur = out[..., q0 - 1].contiguous()
-        new_gpd = out.reshape((Fout, nx, nxi) + extra + (nq_tot,))
+            cur = out[:, :, :, q0 - 1, :].contiguous()
+        new_gpd = out.permute(0, 1, 2, 4, 3).reshape((Fout, nx, nxi) + extra + (nq_tot,))
         return new_gpd
 
     ## ~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~
@@ -315,7 +316,8 @@ def _storage(M):
 
 
 def _fused_fixed_flavor(gpd_in, M_SG, M_NSp, M_NSm, nfl, out, q0, skip):
-    """tkb_evolve_fixed_flavor: gpd_in (F, nx, nxi, S) contiguous -> out[:, :, :, :, q0 : q0 + nQ2 - skip]"""
+    """tkb_evolve_fixed_flavor: gpd_in (F, nx, nxi, S) contiguous -> out[:, :, :, q0 : q0 + nQ2 - skip, :]
+    (out is stored [flavour][x][xi][Q2][sample])"""
     import ctypes as C
     L = _lib.lib()
     F, nx, nxi, S = (int(v) for v in gpd_in.shape)
@@ -327,7 +329,7 @@ def _fused_fixed_flavor(gpd_in, M_SG, M_NSp, M_NSm, nfl, out, q0, skip):
     work = torch.empty((max(nwork, 1),), dtype=torch.float64, device=gpd_in.device)
     _lib.check(L.tkb_evolve_fixed_flavor(nx, nxi, nq, S, nfl, F, int(out.shape[0]), T.ctypes.data_as(_lib._dp),
                                          N.ctypes.data_as(_lib._dp), _lib.ptr(sg), _lib.ptr(nsp), _lib.ptr(nsm),
-                                         _lib.ptr(gpd_in), _lib.ptr(out), int(out.shape[-1]), int(q0), int(skip),
+                                         _lib.ptr(gpd_in), _lib.ptr(out), int(out.shape[3]), int(q0), int(skip),
                                          _lib.ptr(work), _lib.stream_ptr()))
 
 
@@ -344,10 +346,11 @@ def evolve_fixed_flavor(gpd_grid, M_SG, M_NSp, M_NSm, nfl=4):
         S *= e
     nq = int(M_SG.shape[3])
     Fout = max(F, nfl + 1)
-    out = torch.empty((Fout, nx, nxi, S, nq), dtype=torch.float64, device=gpd_grid.device)
+    out = torch.empty((Fout, nx, nxi, nq, S), dtype=torch.float64, device=gpd_grid.device)
     if S > 0:
         _fused_fixed_flavor(gpd_grid.reshape(F, nx, nxi, S).contiguous(), M_SG, M_NSp, M_NSm, nfl, out, 0, 0)
-    return out.reshape((Fout, nx, nxi) + extra + (nq,))
+    # stored with the sample index fastest; the logical shape is the reference's (flavour, x, xi, ..., Q2)
+    return out.permute(0, 1, 2, 4, 3).reshape((Fout, nx, nxi) + extra + (nq,))
 
 
 def evolve_fixed_flavor_unfused(gpd_grid, M_SG, M_NSp, M_NSm, nfl=4):
