@@ -55,6 +55,7 @@ __device__ __forceinline__ void qp_bar_sync_i(int count)
 template <int ID>
 __device__ __forceinline__ void qp_bar_arrive_i(int count)
 {
+    __threadfence_block();               // the producer's shared-memory writes are visible before it is counted as arrived
     asm volatile("bar.arrive %0, %1;" ::"n"(ID), "r"(count) : "memory");
 }
 __device__ __forceinline__ void qp_bar_sync(int id, int count)
