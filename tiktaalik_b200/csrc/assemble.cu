@@ -64,6 +64,23 @@ TKB_DEV double node_eta(double centr, double hlgth, int q)
 // K1: fixed quadrature.  grid = (n, nxi), block = 256 threads.
 // P layout: P[f][ixi][i][j] (row-major n x n per xi).  diag layout: diag[ixi][i][DIAG_N].
 
+// One-argument logs / dilogs of the fixed point x_i (eval_half, FIX): the same for the 126 nodes of row (xi, i) in K1 and
+// for the 21 QAGS instances of that row in K2, so they are computed once per row by a small kernel and read from
+// this table (10 doubles per row: [half][PRE_N] for U = 0.5 (1 +- x_i / xi)).
+__device__ const double* d_pre_tab = nullptr;
+
+__global__ void pre_table_kernel(int n, int nxi, const double* __restrict__ xi_arr, int grid_type, double* __restrict__ tab)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n * nxi * 2 * PRE_N) return;
+    const int row = e / (2 * PRE_N), v = e - row * (2 * PRE_N);
+    const int ixi = row / n, i = row - ixi * n + 1;
+    const double xi = xi_arr[ixi];
+    const double x = grid_node(i, n, xi, grid_type);
+    const double U = (v / PRE_N) ? 0.5 * (1.0 - x / xi) : 0.5 * (1.0 + x / xi);
+    tab[e] = pre_value(v % PRE_N, U);
+}
+
 constexpr int K1_THREADS = 256;
 constexpr int NNODE = 126;
 
@@ -108,8 +125,7 @@ assemble_fixed_kernel(int n, int nxi, const double* __restrict__ xi_arr, int gri
         s_allfinite = 1;
     } else if (tid >= 96 && tid < 96 + 2 * PRE_N) {
         const int v = tid - 96;
-        const double X1 = 0.5 * (1.0 + x / xi), X2 = 0.5 * (1.0 - x / xi);
-        s_pre[v / PRE_N][v % PRE_N] = pre_value(v % PRE_N, (v / PRE_N) ? X2 : X1);
+        s_pre[v / PRE_N][v % PRE_N] = d_pre_tab[((size_t)ixi * n + (size_t)(i - 1)) * (2 * PRE_N) + v];
     }
     __syncthreads();
     if (tid == 0) {
@@ -1177,6 +1193,18 @@ int launch_task_classes(int c, int npts, const double* xs, const double* ys, con
         ++g_launches;                                                        \
         if (e_ != cudaSuccess) return set_error(cudaGetErrorString(e_));     \
     } while (0)
+
+int launch_pre_table(int n, int nxi, const double* xi_dev, int grid_type, double* tab, cudaStream_t st)
+{
+    cudaError_t e = cudaMemcpyToSymbolAsync(d_pre_tab, &tab, sizeof(tab), 0, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
+    const int total = n * nxi * 2 * PRE_N;
+    pre_table_kernel<<<(total + 127) / 128, 128, 0, st>>>(n, nxi, xi_dev, grid_type, tab);
+    ++g_launches;
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
+    return 0;
+}
 
 int set_grid_variant(int eta_recip_f32, int x0_recip_f32)
 {

@@ -289,7 +289,7 @@ assemble_cst_pipe_kernel(int c, int n, int nxi, const double* __restrict__ xi_ar
                 const int s = g * QG + e / (2 * PRE_N), v = e % (2 * PRE_N);
                 const QSlot& S = sh.slot[s];
                 if (S.nint == 1 && ((qp_pre_need<KID>() >> (v % PRE_N)) & 1u))
-                    sh.pre[s][v / PRE_N][v % PRE_N] = pre_value(v % PRE_N, (v / PRE_N) ? S.xx2 : S.xx1);
+                    sh.pre[s][v / PRE_N][v % PRE_N] = d_pre_tab[(size_t)(S.inst / 3ULL) * (2 * PRE_N) + v];   // per-row table
             }
         }
         qp_bar_sync(QP_BAR_EV, NE);

@@ -47,6 +47,7 @@ struct Context {
     double* d_xi = nullptr;
     double* P = nullptr;        // [22][nxi][n][n]
     double* diag = nullptr;     // [nxi][n][DIAG_N]
+    double* pre_tab = nullptr;  // [nxi][n][2][5] one-argument logs / dilogs of the rows' fixed points
     double* cst_res = nullptr;  // [nxi][n][7][3]
     int* cst_last = nullptr;
     int* cst_ifail = nullptr;
@@ -93,6 +94,8 @@ static void free_kernels()
     if (g.d_xi) cudaFree(g.d_xi);
     if (g.P) cudaFree(g.P);
     if (g.diag) cudaFree(g.diag);
+    if (g.pre_tab) cudaFree(g.pre_tab);
+    g.pre_tab = nullptr;
     if (g.cst_res) cudaFree(g.cst_res);
     if (g.cst_last) cudaFree(g.cst_last);
     if (g.cst_ifail) cudaFree(g.cst_ifail);
@@ -147,6 +150,7 @@ static int make_kernels_impl(int nx, int nxi, const double* xi_host, int grid_ty
         CUDA_OK(cudaMalloc(&g.d_xi, sizeof(double) * nxi));
         CUDA_OK(cudaMalloc(&g.P, sizeof(double) * nn * NKERN_));
         CUDA_OK(cudaMalloc(&g.diag, sizeof(double) * rows * DIAG_N));
+        CUDA_OK(cudaMalloc(&g.pre_tab, sizeof(double) * rows * 10));
         CUDA_OK(cudaMalloc(&g.cst_res, sizeof(double) * rows * 21));
         CUDA_OK(cudaMalloc(&g.cst_last, sizeof(int) * rows * 21));
         CUDA_OK(cudaMalloc(&g.cst_ifail, sizeof(int) * rows * 21));
@@ -156,6 +160,7 @@ static int make_kernels_impl(int nx, int nxi, const double* xi_host, int grid_ty
     // K1 (fixed quadrature) and K2 (QAGS constants) are independent.  K2's seven persistent launches go
     // first, K1 runs on its own stream and fills the SMs that K2's draining launches free.
     const bool overlap_k1 = !getenv("TKB_K1_SERIAL");
+    if (launch_pre_table(nx, nxi, g.d_xi, grid_type, g.pre_tab, st)) return 1;
     CUDA_OK(cudaEventRecord(g.ev[0], st));
     if (!overlap_k1) {
         if (launch_assemble_fixed(nx, nxi, g.d_xi, grid_type, g.P, g.diag, st)) return 1;
