@@ -66,19 +66,26 @@ TKB_DEV double node_eta(double centr, double hlgth, int q)
 
 // One-argument logs / dilogs of the fixed point x_i (eval_half, FIX): the same for the 126 nodes of row (xi, i) in K1 and
 // for the 21 QAGS instances of that row in K2, so they are computed once per row by a small kernel and read from
-// this table (10 doubles per row: [half][PRE_N] for U = 0.5 (1 +- x_i / xi)).
+// this table: PRE_ROW doubles per row: [half][PRE_N] for U = 0.5 (1 +- x_i / xi), then x_i and the two U (which the
+// QAGS bookkeeping would otherwise recompute, pow included, at each of the row's 21 instance starts).
+constexpr int PRE_ROW = 16, PRE_X = 10, PRE_U1 = 11, PRE_U2 = 12;
 __device__ const double* d_pre_tab = nullptr;
 
 __global__ void pre_table_kernel(int n, int nxi, const double* __restrict__ xi_arr, int grid_type, double* __restrict__ tab)
 {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n * nxi * 2 * PRE_N) return;
-    const int row = e / (2 * PRE_N), v = e - row * (2 * PRE_N);
+    if (e >= n * nxi * PRE_ROW) return;
+    const int row = e / PRE_ROW, v = e - row * PRE_ROW;
     const int ixi = row / n, i = row - ixi * n + 1;
     const double xi = xi_arr[ixi];
     const double x = grid_node(i, n, xi, grid_type);
-    const double U = (v / PRE_N) ? 0.5 * (1.0 - x / xi) : 0.5 * (1.0 + x / xi);
-    tab[e] = pre_value(v % PRE_N, U);
+    const double U1 = 0.5 * (1.0 + x / xi), U2 = 0.5 * (1.0 - x / xi);
+    double val = 0.0;
+    if (v < 2 * PRE_N) val = pre_value(v % PRE_N, (v / PRE_N) ? U2 : U1);
+    else if (v == PRE_X) val = x;
+    else if (v == PRE_U1) val = U1;
+    else if (v == PRE_U2) val = U2;
+    tab[e] = val;
 }
 
 constexpr int K1_THREADS = 256;
@@ -125,7 +132,7 @@ assemble_fixed_kernel(int n, int nxi, const double* __restrict__ xi_arr, int gri
         s_allfinite = 1;
     } else if (tid >= 96 && tid < 96 + 2 * PRE_N) {
         const int v = tid - 96;
-        s_pre[v / PRE_N][v % PRE_N] = d_pre_tab[((size_t)ixi * n + (size_t)(i - 1)) * (2 * PRE_N) + v];
+        s_pre[v / PRE_N][v % PRE_N] = d_pre_tab[((size_t)ixi * n + (size_t)(i - 1)) * PRE_ROW + v];
     }
     __syncthreads();
     if (tid == 0) {
@@ -1194,11 +1201,12 @@ int launch_task_classes(int c, int npts, const double* xs, const double* ys, con
         if (e_ != cudaSuccess) return set_error(cudaGetErrorString(e_));     \
     } while (0)
 
+size_t pre_table_doubles(size_t rows) { return rows * PRE_ROW; }
 int launch_pre_table(int n, int nxi, const double* xi_dev, int grid_type, double* tab, cudaStream_t st)
 {
     cudaError_t e = cudaMemcpyToSymbolAsync(d_pre_tab, &tab, sizeof(tab), 0, cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
-    const int total = n * nxi * 2 * PRE_N;
+    const int total = n * nxi * PRE_ROW;
     pre_table_kernel<<<(total + 127) / 128, 128, 0, st>>>(n, nxi, xi_dev, grid_type, tab);
     ++g_launches;
     e = cudaGetLastError();

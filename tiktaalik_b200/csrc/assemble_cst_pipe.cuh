@@ -154,10 +154,10 @@ assemble_cst_pipe_kernel(int c, int n, int nxi, const double* __restrict__ xi_ar
                         else {
                             const int sub = (int)(inst % 3ULL);
                             const unsigned long long row = inst / 3ULL;
-                            const int i = (int)(row % (unsigned long long)n) + 1;
                             const int ixi = (int)(row / (unsigned long long)n);
                             const double xi = xi_arr[ixi];
-                            const double x = grid_node(i, n, xi, grid_type);
+                            const double* rowtab = d_pre_tab + (size_t)row * PRE_ROW;       // x_i and 0.5 (1 +- x_i / xi) of the row
+                            const double x = rowtab[PRE_X];
                             const double eps = 1e-15;                        // integration.f90:56-63
                             const double ymin = -1.0 + eps, ymax = 1.0 - eps;
                             double a, b;
@@ -165,8 +165,8 @@ assemble_cst_pipe_kernel(int c, int n, int nxi, const double* __restrict__ xi_ar
                             else if (sub == 1) { a = -fabs(x) + eps; b = fabs(x) - eps; }
                             else { a = fabs(x) + eps; b = ymax; }
                             S.inst = inst; S.x = x; S.xi = xi; S.a = a; S.b = b;
-                            S.xx1 = 0.5 * (1.0 + x / xi);
-                            S.xx2 = 0.5 * (1.0 - x / xi);
+                            S.xx1 = rowtab[PRE_U1];
+                            S.xx2 = rowtab[PRE_U2];
                             S.a1 = a; S.b1 = b; S.a2 = a; S.b2 = b;
                             S.nint = 1;
                         }
@@ -289,7 +289,7 @@ assemble_cst_pipe_kernel(int c, int n, int nxi, const double* __restrict__ xi_ar
                 const int s = g * QG + e / (2 * PRE_N), v = e % (2 * PRE_N);
                 const QSlot& S = sh.slot[s];
                 if (S.nint == 1 && ((qp_pre_need<KID>() >> (v % PRE_N)) & 1u))
-                    sh.pre[s][v / PRE_N][v % PRE_N] = d_pre_tab[(size_t)(S.inst / 3ULL) * (2 * PRE_N) + v];   // per-row table
+                    sh.pre[s][v / PRE_N][v % PRE_N] = d_pre_tab[(size_t)(S.inst / 3ULL) * PRE_ROW + v];   // per-row table
             }
         }
         qp_bar_sync(QP_BAR_EV, NE);

@@ -47,7 +47,7 @@ struct Context {
     double* d_xi = nullptr;
     double* P = nullptr;        // [22][nxi][n][n]
     double* diag = nullptr;     // [nxi][n][DIAG_N]
-    double* pre_tab = nullptr;  // [nxi][n][2][5] one-argument logs / dilogs of the rows' fixed points
+    double* pre_tab = nullptr;  // per (xi, i) row: one-argument logs / dilogs of the fixed point, x_i, 0.5 (1 +- x_i / xi)
     double* cst_res = nullptr;  // [nxi][n][7][3]
     int* cst_last = nullptr;
     int* cst_ifail = nullptr;
@@ -150,7 +150,7 @@ static int make_kernels_impl(int nx, int nxi, const double* xi_host, int grid_ty
         CUDA_OK(cudaMalloc(&g.d_xi, sizeof(double) * nxi));
         CUDA_OK(cudaMalloc(&g.P, sizeof(double) * nn * NKERN_));
         CUDA_OK(cudaMalloc(&g.diag, sizeof(double) * rows * DIAG_N));
-        CUDA_OK(cudaMalloc(&g.pre_tab, sizeof(double) * rows * 10));
+        CUDA_OK(cudaMalloc(&g.pre_tab, sizeof(double) * pre_table_doubles(rows)));
         CUDA_OK(cudaMalloc(&g.cst_res, sizeof(double) * rows * 21));
         CUDA_OK(cudaMalloc(&g.cst_last, sizeof(int) * rows * 21));
         CUDA_OK(cudaMalloc(&g.cst_ifail, sizeof(int) * rows * 21));

@@ -16,6 +16,7 @@ extern long long g_launches;             // kernel launches issued by the librar
 size_t qags_scratch_bytes();
 int assemble_cst_warps_per_block();
 int set_grid_variant(int eta_recip_f32, int x0_recip_f32);
+size_t pre_table_doubles(size_t rows);
 int launch_pre_table(int n, int nxi, const double* xi_dev, int grid_type, double* tab, cudaStream_t st);
 int launch_assemble_fixed(int n, int nxi, const double* xi_dev, int grid_type, double* P, double* diag, cudaStream_t st);
 int launch_assemble_cst(int n, int nxi, const double* xi_dev, int grid_type, void* scratch, int nblocks,
