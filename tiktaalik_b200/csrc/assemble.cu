@@ -114,7 +114,8 @@ assemble_fixed_kernel(int n, int nxi, const double* __restrict__ xi_arr, int gri
     const int ixi = blockIdx.y;
     const int tid = threadIdx.x;
     const double xi = xi_arr[ixi];
-    const double x = grid_node(i, n, xi, grid_type);
+    const double* rowtab = d_pre_tab + ((size_t)ixi * n + (size_t)(i - 1)) * PRE_ROW;   // filled by pre_table_kernel
+    const double x = rowtab[PRE_X];
 
     // set-up, spread over a few threads of different warps (every piece is a chain of dependent log / pow / divisions):
     // integration.f90:27-35 breakpoints in eta space; Lagrange weights; eta of x_i; the row's one-argument logs/dilogs
@@ -132,7 +133,7 @@ assemble_fixed_kernel(int n, int nxi, const double* __restrict__ xi_arr, int gri
         s_allfinite = 1;
     } else if (tid >= 96 && tid < 96 + 2 * PRE_N) {
         const int v = tid - 96;
-        s_pre[v / PRE_N][v % PRE_N] = d_pre_tab[((size_t)ixi * n + (size_t)(i - 1)) * PRE_ROW + v];
+        s_pre[v / PRE_N][v % PRE_N] = rowtab[v];
     }
     __syncthreads();
     if (tid == 0) {
@@ -176,7 +177,7 @@ assemble_fixed_kernel(int n, int nxi, const double* __restrict__ xi_arr, int gri
 #pragma unroll
                 for (int m = 0; m < 6; m++) s_b[k][m] = bb[m];
             }
-            const double X1 = 0.5 * (1.0 + x / xi), X2 = 0.5 * (1.0 - x / xi);
+            const double X1 = rowtab[PRE_U1], X2 = rowtab[PRE_U2];
             const double Y1 = 0.5 * (1.0 + y / xi), Y2 = 0.5 * (1.0 - y / xi);
             if (half == 0) { s_Y[k][0] = Y1; s_Y[k][1] = Y2; }
             const bool safe = node_is_safe(X1, X2, Y1, Y2);
@@ -196,7 +197,7 @@ assemble_fixed_kernel(int n, int nxi, const double* __restrict__ xi_arr, int gri
         for (int idx = tid; idx < nlive; idx += K1_THREADS) {
             const int task = s_live[idx];
             const int k = task >> 1, half = task & 1;
-            const double X1 = 0.5 * (1.0 + x / xi), X2 = 0.5 * (1.0 - x / xi);
+            const double X1 = rowtab[PRE_U1], X2 = rowtab[PRE_U2];
             const double Y1 = s_Y[k][0], Y2 = s_Y[k][1];
             double hv[NKERN];
             if (half == 0) eval_half<MASK_ALL, true, 1>(X1, Y1, X2, Y2, hv, s_pre[0], s_pre[1]);
