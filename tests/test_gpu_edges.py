@@ -176,3 +176,39 @@ def test_many_xi_few_rows_queue_drains(tk, tko):
                 got = res[k, i, c]
                 tot = ((0.0 + got[0]) + got[1]) + got[2]
                 assert tot == v or (np.isnan(tot) and np.isnan(v))
+
+
+def test_free_and_reinitialise(tk):
+    """tkb_free releases every buffer; the next constructor call starts from scratch and gives the same numbers"""
+    xis, Q2 = np.array([0.2, 0.6]), np.array([4.0, 9.0])
+    tk.matrices.initialize_kernels(10, xis, grid_type=2)
+    tk.matrices.initialize_evolution_matrices(Q2, nlo=True)
+    before = tk.matrices.matrix_VSG().clone()
+    L = tk._lib.lib()
+    assert L.tkb_free() == 0
+    assert L.tkb_get_nx() == 0 and L.tkb_get_nq2() == 0
+    with pytest.raises(Exception):
+        tk.matrices.initialize_evolution_matrices(Q2, nlo=True)            # kernels are gone: call order contract
+    tk.matrices.initialize_kernels(10, xis, grid_type=2)
+    tk.matrices.initialize_evolution_matrices(Q2, nlo=True)
+    assert torch.equal(tk.matrices.matrix_VSG(), before)
+
+
+def test_cache_round_trip_feeds_the_application(tk, tmp_path):
+    """matrices saved from the device, loaded back (whole and as a xi block) and applied"""
+    from tiktaalik_b200 import cache
+    nx, xis, Q2 = 12, np.array([0.1, 0.3, 0.5, 0.7]), tk.matrices.Q2space(4.0, 20.0, 3)
+    tk.matrices.initialize_kernels(nx, xis, grid_type=1)
+    tk.matrices.initialize_evolution_matrices(Q2, nlo=True)
+    mats = {"VNS_plus": tk.matrices.matrix_VNS(1), "VNS_minus": tk.matrices.matrix_VNS(-1),
+            "VSG": tk.matrices.matrix_VSG(), "ASG": tk.matrices.matrix_ASG()}
+    cache.save_matrices(str(tmp_path / "m"), mats, nx, xis, Q2, nlo=True, grid_type=1)
+    meta, back = cache.load_matrices(str(tmp_path / "m"))
+    assert meta["nx"] == nx and back["VSG"].is_cuda
+    for k in mats:
+        assert torch.equal(back[k], mats[k])
+    g = torch.rand((2 * nx, 4, 3), dtype=torch.float64, device="cuda")
+    assert torch.equal(tk.matrices.apply_matrix(back["VSG"], g), tk.matrices.apply_matrix(mats["VSG"], g))
+    _, part = cache.load_matrices(str(tmp_path / "m"), xi_slice=slice(1, 3), types=["VSG"])
+    out = tk.matrices.apply_matrix(part["VSG"], g[:, 1:3].contiguous())
+    assert torch.equal(out, tk.matrices.apply_matrix(mats["VSG"], g)[:, 1:3])
