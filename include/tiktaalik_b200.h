@@ -82,6 +82,13 @@ int tkb_alpha(int n, const double* q2_host, double* out_host);
 int tkb_apply(int m, int nxi, int nq2, int64_t S, const double* M_dev, const double* g_dev, int64_t ldg,
               double* out_dev, void* stream);
 
+/* the same for a block of S samples taken out of a larger (m, nxi, S_total) array without copying it
+ * (the inference loop of BASELINE config 4: 10^5 samples do not fit HBM as one output, so they are applied
+ * S at a time): g[j][xi][s] is read at g_dev[j*ldg + xi*xig + s], i.e. ldg = nxi*S_total, xig = S_total and
+ * g_dev points at the block's first sample.  out is contiguous [xi][Q2][i][S] as above. */
+int tkb_apply_strided(int m, int nxi, int nq2, int64_t S, const double* M_dev, const double* g_dev, int64_t ldg,
+                      int64_t xig, double* out_dev, void* stream);
+
 /* replaces evolve_fixed_flavor (tiktaalik/evolution.py:495-514) = make_evo_basis (:435-462) + three applications
  * (:507-509) + make_flv_basis (:465-492) + zero padding (:532-540) for one threshold segment at a fixed number of
  * flavours nfl, fused: one decoupling kernel, three applications, one recoupling kernel.

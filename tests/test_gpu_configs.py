@@ -96,6 +96,57 @@ def test_config_c4_application_at_full_matrix_size(tk):
     assert torch.allclose(comb, out[:, :, :4] + 2.0 * out[:, :, 4:8], rtol=1e-12, atol=1e-12 * float(out.abs().max()))
 
 
+def test_sample_blocks_are_read_in_place(tk):
+    """a block g_all[:, :, s0:s1] of a larger sample array goes to the library with its strides (tkb_apply_strided)
+    and gives the bits of the contiguous copy, for the warp-per-row kernel (m < 40) and the GEMM"""
+    for nx in (12, 40):
+        xis = np.array([0.1, 0.4, 0.8])
+        tk.matrices.initialize_kernels(nx, xis, grid_type=1)
+        tk.matrices.initialize_evolution_matrices(tk.matrices.Q2space(4.0, 30.0, 3), nlo=True)
+        M = tk.matrices.matrix_VSG()
+        g_all = torch.rand((2 * nx, 3, 37), dtype=torch.float64, device="cuda", generator=torch.Generator(device="cuda").manual_seed(5))
+        for s0, s1 in ((0, 37), (3, 4), (5, 12), (20, 37)):
+            blk = g_all[:, :, s0:s1]
+            assert not blk.is_contiguous() or s1 - s0 == 37
+            assert torch.equal(tk.matrices.apply_matrix(M, blk), tk.matrices.apply_matrix(M, blk.contiguous())), (nx, s0, s1)
+        parts = []
+        for s0, s1, o in tk.matrices.apply_matrix_chunks(M, g_all, chunk=8):
+            assert torch.equal(o, tk.matrices.apply_matrix(M, g_all[:, :, s0:s1].contiguous())), (nx, s0)
+            parts.append(o.clone())
+        whole = tk.matrices.apply_matrix(M, g_all)      # another block width may sum in another order
+        assert torch.allclose(torch.cat(parts, dim=2), whole, rtol=1e-12, atol=1e-13 * float(whole.abs().max()))
+        with pytest.raises(ValueError):
+            tk.matrices.f90src.apply_wrap(M, g_all, out=torch.empty(3, device="cuda", dtype=torch.float64))
+
+
+def test_config_c4_all_100000_samples_in_blocks(tk):
+    """BASELINE config 4 at its full sample count: nx = 160, 128 xi, 16 Q2, 10^5 samples (16 GB of input; the
+    262 GB result never exists as a whole) applied 2048 at a time.  Exact per block: the first Q2 point returns
+    the input.  Over the whole run: the sum over samples of the results equals the result of the summed samples."""
+    nx, nxi, nq, S = 160, 128, 16, 100000
+    xis = np.geomspace(1e-3, 0.9, nxi)
+    tk.matrices.initialize_kernels(nx, xis, grid_type=2)
+    tk.matrices.initialize_evolution_matrices(tk.matrices.Q2space(4.0, 10.0, nq), nlo=True)
+    M = tk.matrices.matrix_VNS()
+    gen = torch.Generator(device="cuda").manual_seed(99)
+    g_all = torch.rand((nx, nxi, S), generator=gen, dtype=torch.float64, device="cuda")
+    acc = torch.zeros((nx, nxi, nq), dtype=torch.float64, device="cuda")
+    seen = 0
+    for s0, s1, out in tk.matrices.apply_matrix_chunks(M, g_all, chunk=2048):
+        assert tuple(out.shape) == (nx, nxi, s1 - s0, nq)
+        assert torch.equal(out[..., 0], g_all[:, :, s0:s1])
+        acc += out.sum(dim=2)
+        seen += s1 - s0
+    assert seen == S
+    ref = tk.matrices.apply_matrix(M, g_all.sum(dim=2, keepdim=True))[:, :, 0, :]
+    assert torch.allclose(acc, ref, rtol=1e-9, atol=1e-12 * float(ref.abs().max()))
+    # one block in the middle against einsum on the same matrices
+    s0 = 51200
+    out = tk.matrices.apply_matrix(M, g_all[:, :, s0:s0 + 64])
+    ref = torch.einsum("ijkl,jks->iksl", M, g_all[:, :, s0:s0 + 64])
+    assert torch.allclose(out, ref, rtol=1e-11, atol=1e-12 * float(ref.abs().max()))
+
+
 def test_config_c5_shard_shape_nx320(tk, tko):
     """nx = 320, grid 2 (one GPU's block of the 4096-xi sweep, here 3 xi): exact identities, a few QAGS constants
     and kernel rows against the oracle"""

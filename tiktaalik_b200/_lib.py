@@ -33,6 +33,8 @@ SIGNATURES = {
     "tkb_alpha": (C.c_int, [C.c_int, _dp, _dp]),
     "tkb_apply": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
                             C.c_void_p, C.c_void_p]),
+    "tkb_apply_strided": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
+                                    C.c_void_p, C.c_void_p]),
     "tkb_gk": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "tkb_free": (C.c_int, []),
     "tkb_qags_info": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),

@@ -24,12 +24,12 @@ constexpr int GEMV_WARPS = 8;
 template <int S>
 __global__ void __launch_bounds__(GEMV_WARPS * 32)
 apply_small_kernel(int m, int nq2, const double* __restrict__ M, const double* __restrict__ g, int64_t ldg,
-                   double* __restrict__ out)
+                   int64_t xig, double* __restrict__ out)
 {
     extern __shared__ double s_g[];                 // [S][m]: sample-major so that lanes read consecutive words
     const int b = blockIdx.x;                       // b = k * nq2 + q
     const int k = b / nq2;
-    const double* gk = g + (int64_t)k * S;
+    const double* gk = g + (int64_t)k * xig;
     for (int e = threadIdx.x; e < m * S; e += blockDim.x) {
         const int j = e / S, s = e - j * S;
         s_g[s * m + j] = gk[(int64_t)j * ldg + s];
@@ -68,20 +68,21 @@ apply_small_kernel(int m, int nq2, const double* __restrict__ M, const double* _
 }
 
 template <int S>
-static int launch_small(int m, int nb, int nq2, const double* M, const double* g, int64_t ldg, double* out, cudaStream_t st)
+static int launch_small(int m, int nb, int nq2, const double* M, const double* g, int64_t ldg, int64_t xig, double* out,
+                        cudaStream_t st)
 {
     int ysl = 1;
     while ((long long)nb * ysl < 148LL * 4 && ysl * GEMV_WARPS < m) ysl *= 2;
     dim3 grid(nb, ysl);
     const size_t smem = (size_t)m * S * sizeof(double);
-    apply_small_kernel<S><<<grid, GEMV_WARPS * 32, smem, st>>>(m, nq2, M, g, ldg, out);
+    apply_small_kernel<S><<<grid, GEMV_WARPS * 32, smem, st>>>(m, nq2, M, g, ldg, xig, out);
     cudaError_t e = cudaGetLastError();
     ++g_launches;
     if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
     return 0;
 }
 
-int launch_apply(int m, int nxi, int nq2, int64_t S, const double* M, const double* g, int64_t ldg,
+int launch_apply(int m, int nxi, int nq2, int64_t S, const double* M, const double* g, int64_t ldg, int64_t xig,
                  double* out, cudaStream_t st)
 {
     if (S <= 0) return 0;
@@ -89,19 +90,19 @@ int launch_apply(int m, int nxi, int nq2, int64_t S, const double* M, const doub
     static const int small_max = [] { const char* e = getenv("TKB_APPLY_SMALL_MAX"); const int v = e ? atoi(e) : 0;   /* measured: the cp.async DMMA GEMM with a 16-column tile is faster for every S */ return v < 0 ? 0 : (v > GEMV_MAXS ? GEMV_MAXS : v); }();
     if ((S <= small_max || (m < 40 && S <= GEMV_MAXS)) && (m % 2) == 0 && (size_t)m * S * sizeof(double) <= 48 * 1024) {
         switch ((int)S) {
-        case 1: return launch_small<1>(m, nb, nq2, M, g, ldg, out, st);
-        case 2: return launch_small<2>(m, nb, nq2, M, g, ldg, out, st);
-        case 3: return launch_small<3>(m, nb, nq2, M, g, ldg, out, st);
-        case 4: return launch_small<4>(m, nb, nq2, M, g, ldg, out, st);
-        case 5: return launch_small<5>(m, nb, nq2, M, g, ldg, out, st);
-        case 6: return launch_small<6>(m, nb, nq2, M, g, ldg, out, st);
-        case 7: return launch_small<7>(m, nb, nq2, M, g, ldg, out, st);
-        default: return launch_small<8>(m, nb, nq2, M, g, ldg, out, st);
+        case 1: return launch_small<1>(m, nb, nq2, M, g, ldg, xig, out, st);
+        case 2: return launch_small<2>(m, nb, nq2, M, g, ldg, xig, out, st);
+        case 3: return launch_small<3>(m, nb, nq2, M, g, ldg, xig, out, st);
+        case 4: return launch_small<4>(m, nb, nq2, M, g, ldg, xig, out, st);
+        case 5: return launch_small<5>(m, nb, nq2, M, g, ldg, xig, out, st);
+        case 6: return launch_small<6>(m, nb, nq2, M, g, ldg, xig, out, st);
+        case 7: return launch_small<7>(m, nb, nq2, M, g, ldg, xig, out, st);
+        default: return launch_small<8>(m, nb, nq2, M, g, ldg, xig, out, st);
         }
     }
     if (S > 0x7fffffffLL || ldg > 0x7fffffffLL) return set_error("tkb_apply: S too large for one call; tile over samples");
     // C[b] (m x S) = M[b] (m x m) * g_k (m x S), b = k*nq2 + q, right-hand side shared by nq2 consecutive b
-    return launch_gemm(m, (int)S, m, 1.0, M, m, (int64_t)m * m, g, (int)ldg, S, nq2, nullptr, 0, 0,
+    return launch_gemm(m, (int)S, m, 1.0, M, m, (int64_t)m * m, g, (int)ldg, xig, nq2, nullptr, 0, 0,
                        out, (int)S, (int64_t)m * S, nb, st);
 }
 

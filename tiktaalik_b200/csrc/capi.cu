@@ -491,7 +491,15 @@ int tkb_apply(int m, int nxi, int nq2, int64_t S, const double* M_dev, const dou
               double* out_dev, void* stream)
 {
     if (m < 1 || nxi < 1 || nq2 < 1 || S < 0 || !M_dev || !g_dev || !out_dev) return set_error("tkb_apply: bad arguments");
-    return launch_apply(m, nxi, nq2, S, M_dev, g_dev, ldg, out_dev, (cudaStream_t)stream);
+    return launch_apply(m, nxi, nq2, S, M_dev, g_dev, ldg, S, out_dev, (cudaStream_t)stream);
+}
+
+int tkb_apply_strided(int m, int nxi, int nq2, int64_t S, const double* M_dev, const double* g_dev, int64_t ldg,
+                      int64_t xig, double* out_dev, void* stream)
+{
+    if (m < 1 || nxi < 1 || nq2 < 1 || S < 0 || !M_dev || !g_dev || !out_dev || xig < 0 || ldg < 0)
+        return set_error("tkb_apply_strided: bad arguments");
+    return launch_apply(m, nxi, nq2, S, M_dev, g_dev, ldg, xig, out_dev, (cudaStream_t)stream);
 }
 
 int64_t tkb_evolve_workspace(int nx, int nxi, int nq2, int64_t S, int nfl)

@@ -128,9 +128,10 @@ int launch_evolve_fixed_flavor(int n, int nxi, int nq, int64_t S, int nfl, int F
     ++g_launches;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
-    if (launch_apply(2 * n, nxi, nq, S, M_sg, sg_in, (int64_t)nxi * S, sg_out, st)) return 1;
-    if (nfl > 1 && launch_apply(n, nxi, nq, (int64_t)(nfl - 1) * S, M_nsp, t_in, (int64_t)nxi * (nfl - 1) * S, t_out, st)) return 1;
-    if (launch_apply(n, nxi, nq, (int64_t)nfl * S, M_nsm, qm_in, (int64_t)nxi * nfl * S, qm_out, st)) return 1;
+    if (launch_apply(2 * n, nxi, nq, S, M_sg, sg_in, (int64_t)nxi * S, S, sg_out, st)) return 1;
+    if (nfl > 1 && launch_apply(n, nxi, nq, (int64_t)(nfl - 1) * S, M_nsp, t_in, (int64_t)nxi * (nfl - 1) * S,
+                            (int64_t)(nfl - 1) * S, t_out, st)) return 1;
+    if (launch_apply(n, nxi, nq, (int64_t)nfl * S, M_nsm, qm_in, (int64_t)nxi * nfl * S, (int64_t)nfl * S, qm_out, st)) return 1;
     evolve_recouple_kernel<<<ew_grid((int64_t)u * (nq - skip)), 256, 0, st>>>(n, nxi, nq, S, nfl, Fout, R, sg_out, t_out,
                                                                            qm_out, out, ldq, q0, skip);
     ++g_launches;

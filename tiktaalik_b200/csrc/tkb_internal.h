@@ -66,7 +66,7 @@ int launch_evolve_fixed_flavor(int n, int nxi, int nq, int64_t S, int nfl, int F
                                const double* N, const double* M_sg, const double* M_nsp, const double* M_nsm,
                                const double* gpd, double* out, int64_t ldq, int q0, int skip, double* work,
                                cudaStream_t st);
-int launch_apply(int m, int nxi, int nq2, int64_t S, const double* M, const double* g, int64_t ldg,
+int launch_apply(int m, int nxi, int nq2, int64_t S, const double* M, const double* g, int64_t ldg, int64_t xig,
                  double* out, cudaStream_t st);
 
 // gk.cu

@@ -146,11 +146,13 @@ class _Dummy:
 
     # ---- application: the np.einsum the reference's callers run on the matrices ----
     @staticmethod
-    def apply_wrap(M, g):
+    def apply_wrap(M, g, out=None):
         """out[i, k, ..., q] = sum_j M[i, j, k, q] g[j, k, ...]   (evolution.py:259, examples.py:77).
 
         M: (m, m, nxi, nQ2) as returned by the evomatrix getters (any strides);
-        g: (m, nxi, ...) numpy array or torch tensor.  Returns a CUDA tensor (m, nxi, ..., nQ2).
+        g: (m, nxi, ...) numpy array or torch tensor; a block of samples cut out of a larger (m, nxi, S_total)
+        device array (g_all[:, :, s0:s1]) is read in place.  out: optional contiguous CUDA storage of shape
+        (nxi, nQ2, m, S) to write into (an inference loop reuses it).  Returns a CUDA tensor (m, nxi, ..., nQ2).
         """
         L = _lib.lib()
         dev = _lib.require_cuda()
@@ -170,13 +172,20 @@ class _Dummy:
         store = M.permute(2, 3, 0, 1)             # [xi][Q2][i][j]
         if not store.is_contiguous():
             store = store.contiguous()
-        g2 = g.reshape(m, nxi, S)
-        if not g2.is_contiguous():
-            g2 = g2.contiguous()
-        out = torch.empty((nxi, nq2, m, S), dtype=torch.float64, device=dev)
+        if g.dim() == 3 and S > 0 and (g.stride(2) == 1 or S == 1) and g.stride(0) >= 0 and g.stride(1) >= 0:
+            g2 = g                                # sample block of a larger array: strides go to the library
+        else:
+            g2 = g.reshape(m, nxi, S)
+            if not g2.is_contiguous():
+                g2 = g2.contiguous()
+        if out is None:
+            out = torch.empty((nxi, nq2, m, S), dtype=torch.float64, device=dev)
+        elif (not isinstance(out, torch.Tensor) or tuple(out.shape) != (nxi, nq2, m, S) or out.dtype != torch.float64
+              or not out.is_cuda or not out.is_contiguous()):
+            raise ValueError("apply: out must be a contiguous float64 CUDA tensor of shape %s" % ((nxi, nq2, m, S),))
         if S > 0:
-            _lib.check(L.tkb_apply(int(m), int(nxi), int(nq2), int(S), _lib.ptr(store), _lib.ptr(g2), int(nxi * S),
-                                   _lib.ptr(out), _lib.stream_ptr()))
+            _lib.check(L.tkb_apply_strided(int(m), int(nxi), int(nq2), int(S), _lib.ptr(store), _lib.ptr(g2),
+                                           int(g2.stride(0)), int(g2.stride(1)), _lib.ptr(out), _lib.stream_ptr()))
         return out.permute(2, 0, 3, 1).reshape((m, nxi) + extra + (nq2,))
 
 

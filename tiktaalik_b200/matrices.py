@@ -132,6 +132,25 @@ def apply_matrix(M, gpd):
     an evolution matrix (examples/examples.py:77; evolution.py:259). '''
     return f90src.apply_wrap(M, gpd)
 
+def apply_matrix_chunks(M, gpd, chunk=1024, buffers=2):
+    ''' The inference loop of BASELINE config 4: apply M (m, m, nxi, nQ2) to many samples gpd (m, nxi, S_total),
+    `chunk` samples at a time, because the full result (m, nxi, S_total, nQ2) does not fit HBM for S_total ~ 1e5.
+    Yields (s0, s1, out) with out = apply_matrix(M, gpd[:, :, s0:s1]) of shape (m, nxi, s1 - s0, nQ2).  The
+    sample blocks are read in place and the results rotate through `buffers` preallocated arrays, so the
+    consumer has to be done with a block (on the current stream) `buffers` blocks later. '''
+    import torch
+    m, nxi, S_total = int(gpd.shape[0]), int(gpd.shape[1]), int(gpd.shape[2])
+    nq2 = int(M.shape[3])
+    chunk = max(1, min(int(chunk), S_total)) if S_total > 0 else 1
+    store = M.permute(2, 3, 0, 1)
+    Mc = store.contiguous().permute(2, 3, 0, 1) if not store.is_contiguous() else M
+    ring = [torch.empty((nxi, nq2, m, chunk), dtype=torch.float64, device=M.device) for _ in range(max(1, int(buffers)))]
+    for n, s0 in enumerate(range(0, S_total, chunk)):
+        s1 = min(S_total, s0 + chunk)
+        buf = ring[n % len(ring)]
+        out = buf if s1 - s0 == chunk else buf.view(-1)[: nxi * nq2 * m * (s1 - s0)].view(nxi, nq2, m, s1 - s0)
+        yield s0, s1, f90src.apply_wrap(Mc, gpd[:, :, s0:s1], out=out)
+
 # ~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~
 # Routines to create kernels (reference: matrices.py:190-276)
 

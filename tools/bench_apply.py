@@ -53,6 +53,27 @@ for name, M in mats.items():
         flop = 2.0 * m * m * nxi * nq * S
         print("%s m=%d S=%5d  %8.3f ms  %8.1f GB/s (%.2f of HBM)  %6.2f TFLOP/s (%.2f of FP64)  %.3e evolved GPDs/s"
               % (name, m, S, t * 1e3, byt / t / 1e9, byt / t / 1e9 / hbm, flop / t / 1e12, flop / t / 1e12 / peak.value, S / t))
+# config C4 at its full sample count: 10^5 samples, applied in blocks that are read in place, results rotating
+# through two buffers (the 262 / 1049 GB result never exists as a whole); one timed pass over all samples
+S_total = int(os.environ.get("TKB_C4_SAMPLES", "100000"))
+for name, M in mats.items():
+    m = M.shape[0]
+    g_all = torch.rand((m, nxi, S_total), generator=gen, dtype=torch.float64, device="cuda")
+    for chunk in (1024, 2048):
+        for _ in tk.matrices.apply_matrix_chunks(M, g_all[:, :, : 2 * chunk], chunk=chunk):
+            pass
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in tk.matrices.apply_matrix_chunks(M, g_all, chunk=chunk):
+            pass
+        e1.record()
+        torch.cuda.synchronize()
+        t = e0.elapsed_time(e1) * 1e-3
+        flop = 2.0 * m * m * nxi * nq * S_total
+        print("%s m=%d S=%d in blocks of %d: %.3f s  %.3e evolved GPDs/s  %.2f TFLOP/s (%.2f of FP64)"
+              % (name, m, S_total, chunk, t, S_total / t, flop / t / 1e12, flop / t / 1e12 / peak.value))
+    del g_all
 ms = (C.c_double * 3)()
 _lib.check(L.tkb_stage_ms(ms))
 flop_step = 144.0 * nx ** 3 * nxi * (nq - 1)
