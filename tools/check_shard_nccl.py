@@ -39,6 +39,34 @@ for n, ref in full.items():
     if not same:
         print("rank %d: C-ABI gather of %s differs" % (rank, n))
     ok = ok and same
+# bandwidth of the one exchange step at the bench's size (nx = 160, 256 xi per rank, Q2 4 -> 10): each rank
+# receives (world - 1) slabs of every matrix family over NVLink; device-timed, max over ranks
+if len(sys.argv) > 1 and sys.argv[1] == "--bw":
+    nxb, per = 160, 256
+    xib = np.geomspace(2e-5, 0.5, per * world)
+    tk.shard.initialize_kernels_sharded(nxb, xib, grid_type=2, rank=rank, world_size=world)
+    tk.matrices.initialize_evolution_matrices(np.array([4.0, 10.0]), nlo=True)
+    cb, _ = tk.shard.xi_partition(xib.shape[0], world)
+    for n in ("matrix_VNS", "matrix_VSG"):
+        m = nxb * (2 if n.endswith("SG") else 1)
+        recv = 8.0 * m * m * 2 * per * (world - 1)
+        best = None
+        for rep in range(6):
+            dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            got = tk.shard.gather_matrix_capi(n, cb)
+            e1.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            if rep and (best is None or t.item() < best):
+                best = t.item()
+            del got
+        if rank == 0:
+            print("all-gather of %s over %d GPUs: %.1f MB received per rank in %.3f ms = %.1f GB/s per rank (incl. allocation of the result)"
+                  % (n, world, recv / 1e6, best, recv / best / 1e6))
 tk._lib.lib().tkb_shard_finalize()
 flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
