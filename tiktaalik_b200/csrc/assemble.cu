@@ -365,7 +365,7 @@ struct QagsShared {                      // per-warp shared state
 };
 
 #ifdef TKB_K2_STATS
-__device__ unsigned long long g_k2stats[16];
+__device__ unsigned long long g_k2stats[24];
 #define K2_T0() long long t0_ = clock64()
 #define K2_ACC(slot) do { if (lane == 0) atomicAdd(&g_k2stats[slot], (unsigned long long)(clock64() - t0_)); t0_ = clock64(); } while (0)
 #define K2_CNT(slot, v) do { if (lane == 0) atomicAdd(&g_k2stats[slot], (unsigned long long)(v)); } while (0)
@@ -1377,13 +1377,15 @@ static int launch_pipe_one(int c, int n, int nxi, const double* xi_dev, int grid
 #ifdef TKB_K2_STATS
     {
         cudaStreamSynchronize(st);
-        unsigned long long h[16];
+        unsigned long long h[24];
         cudaMemcpyFromSymbol(h, g_k2stats, sizeof h);
+        fprintf(stderr, "K2 pipe phases KID %d: node pass %.0f, evaluation %.0f, K(x,y)-K(y,x) %.0f cyc per group-round; tasks per group-round %.1f\n",
+                KID, h[6] ? (double)h[16] / h[6] : 0., h[6] ? (double)h[17] / h[6] : 0., h[6] ? (double)h[18] / h[6] : 0., h[6] ? (double)h[19] / h[6] : 0.);
         fprintf(stderr, "K2 pipe stats KID %d: bookkeeper per round: wait-values %.0f, bookkeeping %.0f, wait-REQ %.0f cyc (%llu rounds) | evaluators per round: wait-requests %.0f, work %.0f cyc (%llu rounds) | block lifetime %.3g cyc, of which draining after the queue ran dry %.3g (%.1f %%)\n",
                 KID, h[3] ? (double)h[0] / h[3] : 0., h[3] ? (double)h[1] / h[3] : 0., h[3] ? (double)h[2] / h[3] : 0., h[3],
                 h[6] ? (double)h[4] / h[6] : 0., h[6] ? (double)h[5] / h[6] : 0., h[6], (double)h[7], (double)h[15],
                 h[7] ? 100.0 * (double)h[15] / (double)h[7] : 0.0);
-        unsigned long long z[16] = { 0 };
+        unsigned long long z[24] = { 0 };
         cudaMemcpyToSymbol(g_k2stats, z, sizeof z);
     }
 #endif

@@ -293,6 +293,9 @@ assemble_cst_pipe_kernel(int c, int n, int nxi, const double* __restrict__ xi_ar
             }
         }
         qp_bar_sync(QP_BAR_EV, NE);
+#ifdef TKB_K2_STATS
+        const long long tp1_ = clock64();
+#endif
 
         // ---- E: evaluate the live half kernels.  Four segments (direction x {full, erbl-only}), each padded
         // to whole warps so that a warp runs one variant; the warps draw 32-task chunks from a counter, most
@@ -331,6 +334,10 @@ assemble_cst_pipe_kernel(int c, int n, int nxi, const double* __restrict__ xi_ar
             }
         }
         qp_bar_sync(QP_BAR_EV, NE);
+#ifdef TKB_K2_STATS
+        const long long tp2_ = clock64();
+        const int ntask_ = sh.nfull[g][0] + sh.nfull[g][1] + sh.nerbl[g][0] + sh.nerbl[g][1];
+#endif
 
         // ---- K: K(x,y,xi) - K(y,x,xi) per node ----
         for (int e = etid; e < QG * 42; e += NE) {
@@ -349,6 +356,10 @@ assemble_cst_pipe_kernel(int c, int n, int nxi, const double* __restrict__ xi_ar
             atomicAdd(&g_k2stats[4], (unsigned long long)(te1_ - te0_));              // evaluators wait for requests
             atomicAdd(&g_k2stats[5], (unsigned long long)(clock64() - te1_));         // N+C, E, K
             atomicAdd(&g_k2stats[6], 1ULL);
+            atomicAdd(&g_k2stats[16], (unsigned long long)(tp1_ - te1_));             // node pass
+            atomicAdd(&g_k2stats[17], (unsigned long long)(tp2_ - tp1_));             // evaluation
+            atomicAdd(&g_k2stats[18], (unsigned long long)(clock64() - tp2_));        // K(x,y) - K(y,x)
+            atomicAdd(&g_k2stats[19], (unsigned long long)ntask_);
         }
 #endif
     }
