@@ -3,8 +3,8 @@
 // the reference is independent across xi (matevo.f90:291,325,359,381,426,452,514,550,584; evolution.py:507-509).
 //
 // The library stores M as [xi][Q2][i][j], so a rank's contribution is one contiguous slab and the gathered
-// array is the concatenation of the slabs in rank order.  Block sizes may differ between ranks, so the gather is
-// one NCCL group of `world` broadcasts (root r writes slab r), in place for the caller's own slab.
+// array is the concatenation of the slabs in rank order.  Equal blocks go through ncclAllGather; when the block
+// sizes differ between ranks the gather is one NCCL group of `world` broadcasts (root r writes slab r).
 //
 // NCCL is bound at run time (dlopen of libnccl.so.2 -- inside a PyTorch process that is the copy torch has
 // already loaded) so that the library has no link-time dependency on it and single-GPU use never touches it.
@@ -30,6 +30,7 @@ struct Nccl {
     int (*GroupStart)() = nullptr;
     int (*GroupEnd)() = nullptr;
     int (*Broadcast)(const void*, void*, size_t, int, int, Comm, cudaStream_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, Comm, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
     Comm comm = nullptr;
     int rank = 0, world = 1;
@@ -57,6 +58,7 @@ int load_nccl()
     TKB_SYM(GroupStart, "ncclGroupStart")
     TKB_SYM(GroupEnd, "ncclGroupEnd")
     TKB_SYM(Broadcast, "ncclBroadcast")
+    TKB_SYM(AllGather, "ncclAllGather")
     TKB_SYM(GetErrorString, "ncclGetErrorString")
 #undef TKB_SYM
     N.handle = h;
@@ -111,6 +113,13 @@ int tkb_allgather_matrices(int type, int nstype, const int* nxi_per_rank, double
     const int64_t m = shape[0], nxi = shape[2], nq2 = shape[3];
     if (nxi_per_rank[N.rank] != nxi) return tkb::set_error("tkb_allgather_matrices: nxi_per_rank[rank] differs from the assembled xi count");
     const size_t per_xi = (size_t)nq2 * (size_t)m * (size_t)m;
+    bool even = true;
+    for (int r = 0; r < N.world; r++) even = even && (nxi_per_rank[r] == nxi_per_rank[0]);
+    if (even) {         // equal blocks: one all-gather (all NVLink ports at once; 8 grouped broadcasts reach a fraction of it)
+        const int rc1 = N.AllGather(local, dev_out, (size_t)nxi * per_xi, kNcclFloat64, N.comm, (cudaStream_t)stream);
+        if (rc1 != 0) return nccl_fail("ncclAllGather", rc1);
+        return 0;
+    }
     int rc = N.GroupStart();
     if (rc != 0) return nccl_fail("ncclGroupStart", rc);
     size_t off = 0;

@@ -102,16 +102,20 @@ def init_capi(group=None):
     _lib.check(_lib.lib().tkb_shard_init(box[0], rank, world))
 
 
-def gather_matrix_capi(name, counts, ns_type=1):
+def gather_matrix_capi(name, counts, ns_type=1, out=None):
     """All-gather one matrix family along xi with tkb_allgather_matrices.  name: 'matrix_VNS' | 'matrix_VSG' |
-    'matrix_ANS' | 'matrix_ASG'; counts: xi block sizes of all ranks.  Returns (m, m, nxi_total, nQ2)."""
+    'matrix_ANS' | 'matrix_ASG'; counts: xi block sizes of all ranks; out: optional contiguous
+    (nxi_total, nQ2, m, m) CUDA storage to gather into.  Returns (m, m, nxi_total, nQ2)."""
     import ctypes as C
     from . import _lib
     L = _lib.lib()
     n, nq = L.tkb_get_nx(), L.tkb_get_nq2()
     m = n * (2 if name.endswith("SG") else 1)
     total = int(sum(counts))
-    out = torch.empty((total, nq, m, m), dtype=torch.float64, device=_lib.require_cuda())
+    if out is None:
+        out = torch.empty((total, nq, m, m), dtype=torch.float64, device=_lib.require_cuda())
+    elif tuple(out.shape) != (total, nq, m, m) or out.dtype != torch.float64 or not out.is_cuda or not out.is_contiguous():
+        raise ValueError("gather_matrix_capi: out must be a contiguous float64 CUDA tensor of shape %s" % ((total, nq, m, m),))
     cnt = (C.c_int * len(counts))(*[int(c) for c in counts])
     _lib.check(L.tkb_allgather_matrices(_MATRIX_TYPES[name], int(ns_type), cnt, C.c_void_p(out.data_ptr()),
                                         _lib.stream_ptr()))
