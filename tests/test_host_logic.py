@@ -132,3 +132,14 @@ def test_matrix_cache_round_trip(tmp_path):
     assert torch.equal(part["VNS_plus"], mats["VNS_plus"][:, :, 1:3, :]) and len(meta3["xi"]) == 2
     with pytest.raises(ValueError):
         cache.save_matrices(str(tmp_path / "d"), {"bogus": mats["VSG"]}, nx, xi, [4.0, 6.0, 10.0], nlo=True)
+
+
+def test_integration_document_names_every_c_abi_entry():
+    """INTEGRATION.md is the binding guide: every function include/tiktaalik_b200.h declares appears in it"""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, "include", "tiktaalik_b200.h")).read()
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    names = sorted(set(re.findall(r"\b(tkb_[a-z0-9_]+)\s*\(", header)))
+    assert len(names) > 25
+    assert [n for n in names if n not in doc] == []
