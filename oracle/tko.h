@@ -8,8 +8,9 @@
  * PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures for this
  * path and it cannot be built here (no Fortran compiler),
  * so this restatement is pinned only by reference-independent known-answer tests
- * (mpmath dilogarithm, SciPy QUADPACK, block identities, polynomiality, sum rules, and
- * the forward limit xi -> 0 against the published LO/NLO DGLAP splitting functions); see
+ * (mpmath dilogarithm, SciPy QUADPACK, block identities, polynomiality, sum rules, the
+ * forward limit xi -> 0 against the published LO/NLO DGLAP splitting functions, and at
+ * xi != 0 the conformal-moment mixing: LO singlet, NLO non-singlet (Mueller 1994)); see
  * tests/test_oracle_known_answers.py, tests/splitting_functions.py and DESIGN.md.
  */
 #ifndef TKO_H

@@ -275,6 +275,98 @@ def test_lo_conformal_moments_are_eigenfunctions(tko, xi):
             assert abs(val + 0.5 * gamma * c(y)) < 1e-10 * max(1.0, abs(c(y))), (n, y, val, -0.5 * gamma * c(y))
 
 
+@pytest.mark.parametrize("xi", [0.3, 0.7])
+def test_lo_singlet_conformal_moments_mix_with_the_forward_anomalous_dimensions(tko, xi):
+    """The LO singlet kernels at any xi: with c_n^q = xi^n C_n^{3/2}(x/xi) and c_n^g = xi^(n-1) C_(n-1)^{5/2}(x/xi)
+    (n odd; the gluon GPD is normalised to x g(x) forward) conformal symmetry makes
+
+        int dx c_n^q(x) K_qG(x, y, xi)              = (3/n) P_qg(N) c_n^g(y)        (per flavour)
+        int dx c_n^g(x) K_Gq(x, y, xi)              = (n/3) P_gq(N) c_n^q(y)
+        int dx [c_n^g(x) - c_n^g(y)] K_GG(x, y, xi) = [P_gg(N) - DeltaP_gg(2)] c_n^g(y)   (n_f-free parts, no delta term)
+
+    with N = n + 1 and the forward LO splitting-function moments, unpolarised for the V type and polarised for the A
+    type; the factors 3/n, n/3 are the ratio of the Gegenbauer normalisations.  The right-hand constants must not
+    depend on y (ERBL, DGLAP, either sign) or xi: this fixes the xi dependence of KA0_qG, KVmA0_qG, KA0_Gq, KVmA0_Gq,
+    KA0_GG and KVmA0_GG, which the forward limit cannot see."""
+    gegenbauer = pytest.importorskip("scipy.special").gegenbauer
+    CF, CA, TF = 4.0 / 3.0, 3.0, 0.5
+    k = lambda name, x, y: tko.kernel(name, x, y, xi)
+    for n in (1, 3, 5):
+        N = n + 1
+        S1 = sum(1.0 / j for j in range(1, N + 1))
+        P = {"V": (2 * TF * (N * N + N + 2) / (N * (N + 1) * (N + 2)), CF * (N * N + N + 2) / ((N - 1) * N * (N + 1)),
+                   2 * CA * (1.0 / (N * (N - 1)) + 1.0 / ((N + 1) * (N + 2)) - S1) + 11 * CA / 6),
+             "A": (2 * TF * (N - 1) / (N * (N + 1)), CF * (N + 2) / (N * (N + 1)),
+                   CA * (11.0 / 6 + 4.0 / (N * (N + 1)) - 2 * S1))}
+        dPgg2 = CA * (11.0 / 6 + 4.0 / 6 - 3.0)
+        Cq, Cg = gegenbauer(n, 1.5), gegenbauer(n - 1, 2.5)
+        cq = lambda x: xi ** n * Cq(x / xi)
+        cg = lambda x: xi ** (n - 1) * Cg(x / xi)
+        for y in ((0.15, -0.4) if xi == 0.3 else (0.55, -0.2)):
+            qG_A = _xint(lambda x: cq(x) * k("KA0_qG_reg", x, y), y, xi)
+            qG_D = _xint(lambda x: cq(x) * k("KVmA0_qG_reg", x, y), y, xi)
+            Gq_A = _xint(lambda x: cg(x) * k("KA0_Gq_reg", x, y), y, xi)
+            Gq_D = _xint(lambda x: cg(x) * k("KVmA0_Gq_reg", x, y), y, xi)
+            GG_A = _xint(lambda x: (cg(x) - cg(y)) * k("KA0_GG_pls", x, y), y, xi)
+            GG_D = _xint(lambda x: cg(x) * k("KVmA0_GG_reg", x, y), y, xi)
+            got = {"A": (qG_A / cg(y), Gq_A / cq(y), GG_A / cg(y)),
+                   "V": ((qG_A + qG_D) / cg(y), (Gq_A + Gq_D) / cq(y), (GG_A + GG_D) / cg(y))}
+            for typ in ("A", "V"):
+                pqg, pgq, pgg = P[typ]
+                ref = (3.0 / n * pqg, n / 3.0 * pgq, pgg - dPgg2)
+                for g_, r_ in zip(got[typ], ref):
+                    assert abs(g_ - r_) < 2e-9 * max(1.0, abs(r_)), (typ, n, y, got[typ], ref)
+
+
+def _conformal_mixing(tko, name, n, xi, ys):
+    """coefficients G_nk of  int dx [c_n(x) - c_n(y)] K(x, y, xi) = sum_k G_nk xi^(n-k) c_k(y),  k = n, n-2, ..."""
+    gegenbauer = pytest.importorskip("scipy.special").gegenbauer
+    Cn = gegenbauer(n, 1.5)
+    c = lambda x: xi ** n * Cn(x / xi)
+    I = np.array([_xint(lambda x: (c(x) - c(y)) * tko.kernel(name, x, y, xi), y, xi) for y in ys])
+    ks = list(range(n, -1, -2))
+    A = np.array([[xi ** n * gegenbauer(k, 1.5)(y / xi) for k in ks] for y in ys])
+    coef = np.linalg.lstsq(A, I, rcond=None)[0]
+    assert np.abs(A @ coef - I).max() < 1e-9 * np.abs(I).max()            # a polynomial of that parity and degree
+    return dict(zip(ks, coef))
+
+
+@pytest.mark.parametrize("xi,n", [(0.3, 2), (0.3, 3), (0.3, 5), (0.7, 4)])
+def test_nlo_non_singlet_conformal_mixing_matches_mueller(tko, xi, n):
+    """The xi dependence of the NLO non-singlet kernels.  Beyond LO the conformal moments c_n = xi^n C_n^{3/2}(x/xi)
+    mix with the lower ones, d F_n / d ln Q^2 = -(1/2) sum_k [a g0 + a^2 g1]_nk xi^(n-k) F_k (a = alpha_s / 2 pi), and
+    conformal constraints fix the non-diagonal part in closed form from one-loop quantities (D. Mueller, Phys. Rev.
+    D49 (1994) 2525; Belitsky, Mueller, Nucl. Phys. B527 (1998) 207), for n > k, n - k even:
+
+        g1_nk = (g0_n - g0_k) [ d_nk (beta0 - g0_k) + g_nk ],    beta0 = (2/3) nf - (11/3) CA,
+        d_nk  = -(2k+3) / ((n-k)(n+k+3)),
+        g_nk  = 2 CF d_nk [ 2 A_nk + (A_nk - psi(n+2) + psi(1)) (n-k)(n+k+3) / ((k+1)(k+2)) ],
+        A_nk  = psi((n+k+4)/2) - psi((n-k)/2) + 2 psi(n-k) - psi(n+2) - psi(1),
+        g0_n  = CF (4 S_1(n+1) - 3 - 2/((n+1)(n+2))).
+
+    The oracle's KV1_NSp, KV1_NSm (nf-free part) and KV1_NS_nfl (per flavour) must reproduce it for every k, and the
+    two signatures must have the same non-diagonal part (the formula does not know about them)."""
+    from scipy.special import digamma as psi
+    CF, CA = 4.0 / 3.0, 3.0
+    g0 = lambda m: CF * (4 * sum(1.0 / j for j in range(1, m + 2)) - 3 - 2.0 / ((m + 1) * (m + 2)))
+    ys = np.array([-0.85, -0.5, -0.12, 0.2, 0.41, 0.62, 0.9])
+    got_p = _conformal_mixing(tko, "KV1_NSp_pls", n, xi, ys)
+    got_m = _conformal_mixing(tko, "KV1_NSm_pls", n, xi, ys)
+    got_f = _conformal_mixing(tko, "KV1_NS_pls_nfl", n, xi, ys)
+    for k in range(n - 2, -1, -2):
+        d = -(2 * k + 3.0) / ((n - k) * (n + k + 3))
+        A = psi((n + k + 4) / 2.0) - psi((n - k) / 2.0) + 2 * psi(n - k) - psi(n + 2) - psi(1)
+        g = 2 * CF * d * (2 * A + (A - psi(n + 2) + psi(1)) * (n - k) * (n + k + 3) / ((k + 1.0) * (k + 2)))
+        nd0 = (g0(n) - g0(k)) * (d * (-11.0 / 3 * CA - g0(k)) + g)
+        nd1 = (g0(n) - g0(k)) * d * (2.0 / 3)
+        # float32 rationals of the reference (11./3., 4./3. ...) limit the agreement to a few 1e-8
+        assert abs(got_p[k] + 0.5 * nd0) < 3e-7 * abs(nd0), (n, k, got_p[k], -0.5 * nd0)
+        assert abs(got_f[k] + 0.5 * nd1) < 3e-7 * abs(nd1), (n, k, got_f[k], -0.5 * nd1)
+        assert abs(got_p[k] - got_m[k]) < 1e-9 * abs(nd0), (n, k)
+    # the diagonal entries differ between the signatures (and are what the forward-limit tests pin)
+    assert abs(got_p[n] - got_m[n]) > 1e-3
+
+
 @pytest.mark.parametrize("x,y", FWD_POINTS)
 def test_forward_limit_polarised_singlet_nlo(tko, x, y):
     """A-type NLO singlet entries against Delta P^(1) of Mertig-van Neerven / Vogelsang, normalisation (alpha_s / 2 pi)^2
