@@ -103,3 +103,59 @@ def test_rows_against_oracle_at_full_size(built, tko):
             tot = ((0.0 + got[0]) + got[1]) + got[2]
             assert list(last[k, i, cst]) == l and (tot == v or (np.isnan(tot) and np.isnan(v))), (k, i, cst)
     assert int(last.max()) == 500                              # the V-type gluon constant hits QUADPACK's limit at xi = 2e-5
+
+
+# --------------------------------------------------------------------------------------------
+# Full-matrix parity at the benchmark's own shapes (matevo.f90:283-480 assembly, :485-673 stepping): every raw kernel
+# array for nfl = 3, 4, 5 bit for bit, every QAGS instance's (result, last, ifail), and the NLO evolution matrices
+# within the north-star tolerance -- at nx = 160 (C3/C4) and nx = 320 (C5), grid 2, including xi = 2e-5.
+
+HEADLINE = [(160, [2e-5, 1e-3, 0.3]), (320, [2e-5, 0.45])]
+
+
+def _full_parity(tk, tko, nx, xis, variant=(0, 0), with_qags=True, with_matrices=True):
+    from test_gpu_parity import close, _raw_gpu, _qags_gpu
+    xis = np.array(xis)
+    f90 = tk.f90wrap.matrices.dummy
+    try:
+        f90.set_variant(*variant)
+        tko.set_variant(*variant)
+        tk.matrices.initialize_kernels(nx, xis, grid_type=2)
+        tko.initialize_kernels(nx, xis, 2, mode=1)
+        if with_qags:
+            res, last, ifail = _qags_gpu(tk)
+            for k, s in enumerate(xis):
+                xs = tko.grid_nodes(nx, s, 2)
+                for i in range(nx):
+                    for c in range(7):
+                        v, l, e = tko.cst_integral(c, xs[i], s)
+                        assert list(last[k, i, c]) == l and list(ifail[k, i, c]) == e, (k, i, c, last[k, i, c], l)
+                        got = res[k, i, c]
+                        tot = ((0.0 + got[0]) + got[1]) + got[2]
+                        assert tot == v or (np.isnan(tot) and np.isnan(v)), (k, i, c, tot, v)
+        for nfl in (3, 4, 5):
+            for which, name in enumerate(tko.RAW_NAMES):
+                got = _raw_gpu(tk, which, nfl)
+                ref = tko.raw_kernel(name, nfl)
+                assert np.array_equal(got, ref, equal_nan=True), "%s nfl=%d nx=%d not bit-identical" % (name, nfl, nx)
+        if with_matrices:
+            Q2 = np.array([4.0, 10.0])
+            tk.matrices.initialize_evolution_matrices(Q2, nlo=True)
+            tko.initialize_evolution_matrices(Q2, nlo=True)
+            for name, kw in (("matrix_VNS", {"ns_type": 1}), ("matrix_VNS", {"ns_type": -1}), ("matrix_VSG", {}),
+                             ("matrix_ASG", {})):
+                close(getattr(tk.matrices, name)(**kw).cpu().numpy(), getattr(tko, name)(**kw))
+    finally:
+        f90.set_variant(0, 0)
+        tko.set_variant(0, 0)
+
+
+@pytest.mark.parametrize("nx,xis", HEADLINE)
+def test_full_matrix_parity_at_headline_sizes(tk, tko, nx, xis):
+    _full_parity(tk, tko, nx, xis)
+
+
+@pytest.mark.parametrize("variant", [(1, 0), (0, 1)])
+def test_ofast_variants_at_nx160(tk, tko, variant):
+    """the two float32-division variants of an -Ofast reference build at the benchmark's grid"""
+    _full_parity(tk, tko, 160, [2e-5, 0.3], variant=variant, with_qags=False, with_matrices=False)

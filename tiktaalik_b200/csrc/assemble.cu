@@ -1,5 +1,5 @@
 // assemble.cu -- kernel-matrix assembly on sm_100a: K1 fixed Gauss-Kronrod quadrature,
-// K2 warp-cooperative QAGS for the NLO plus-prescription constants, K3 composition into the
+// K2 batched QAGS for the NLO plus-prescription constants, K3 composition into the
 // nfl-dependent kernel matrices.  Compiled with -fmad=false (see tkb_fp.cuh).
 //
 // Reference path replaced (file:line):
@@ -16,10 +16,10 @@
 //     replays qk21's accumulation per column from shared memory.  Per-term values and the
 //     summation order are those of the reference, so entries agree bit for bit with a
 //     straight evaluation, at 1/nx of the kernel evaluations.
-//   * K2 runs one QAGS instance per warp: the 2 x 21 nodes of a bisection step are 168
-//     half-kernel tasks spread over the lanes; the scalar QUADPACK bookkeeping (qsort, qextr)
-//     runs on lane 0 on per-warp interval lists.  Control flow is QUADPACK's, comparison for
-//     comparison, so the bisection path is the reference's.
+//   * K2 runs batches of QAGS instances per block, split by role (assemble_cst_pipe.cuh): the 2 x 21 nodes
+//     of a bisection step are 168 half-kernel tasks evaluated by the block's evaluator warps, the scalar
+//     QUADPACK bookkeeping (qsort, qextr) runs on bookkeeping warps, one lane pair per instance.  Control
+//     flow is QUADPACK's, comparison for comparison, so the bisection path is the reference's.
 #include <cstdio>
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -332,47 +332,22 @@ assemble_fixed_kernel(int n, int nxi, const double* __restrict__ xi_arr, int gri
 }
 
 // ---------------------------------------------------------------------------------------
-// K2: QAGS (integration.f90:246-904), one instance per warp, one kernel launch per constant.
-//
-// Interval lists: the first QCAP entries of alist/blist/rlist/elist/iord live in shared
-// memory (typical instances need 25-60 intervals), entries beyond spill to a per-warp global
-// scratch (the reference's limit is 500, reached by the round-off dominated V-type gluon
-// constants at xi ~ 2e-5).
-// Evaluation: a bisection step needs the integrand at 2 x 21 nodes = 168 half-kernel tasks
-// (node, direction K(x,y) / K(y,x), half).  A half kernel whose support steps rho_step and
-// erbl_step both vanish is exactly zero (every piece is multiplied by one of them), so the
-// tasks are first classified, the live ones compacted with a warp ballot, and only those are
-// evaluated, 32 at a time.  A task is only skipped when every denominator and log argument of
-// any half kernel is non-zero (`safe`), so a 0*Inf = NaN of the reference is still reproduced.
+// K2: QAGS (integration.f90:246-904).  This file holds QUADPACK's scalar routines (qsort, qextr, the qk21 sums) as
+// device code; the per-instance state and the bisection step are in qags_step.cuh, the kernels in
+// assemble_cst_pipe.cuh (default) and assemble_cst_queue.cuh.
+// Interval lists: the first entries of alist/blist/rlist/elist/iord live in shared memory (typical instances need
+// 25-60 intervals), entries beyond spill to a per-slot global scratch (the reference's limit is 500, reached by the
+// round-off dominated V-type gluon constants at xi ~ 2e-5).
+// Evaluation: a bisection step needs the integrand at 2 x 21 nodes = 168 half-kernel tasks (node, direction
+// K(x,y) / K(y,x), half).  A half kernel whose support steps rho_step and erbl_step both vanish is exactly zero
+// (every piece is multiplied by one of them), so the tasks are first classified, the live ones compacted, and only
+// those are evaluated.  A task is only skipped when every denominator and log argument of any half kernel is
+// non-zero (`safe`), so a 0*Inf = NaN of the reference is still reproduced.
 
 constexpr int QLIMIT = 500;
-constexpr int QCAP = 64;                 // indices 1..QCAP-1 in shared memory
-
-struct QagsScratch {                     // per-warp global spill (1-based indices >= QCAP)
-    double alist[QLIMIT + 1], blist[QLIMIT + 1], rlist[QLIMIT + 1], elist[QLIMIT + 1];
-    int iord[QLIMIT + 1];
-};
-size_t qags_scratch_bytes() { return sizeof(QagsScratch); }
-
-struct QagsShared {                      // per-warp shared state
-    double alist[QCAP], blist[QCAP], rlist[QCAP], elist[QCAP];
-    double rlist2[53];
-    double fv[42];                       // integrand at the nodes of the current step
-    double hv[168];                      // half-kernel values of the current step
-    double ny[42][2];                    // per node: 0.5 (1 + y/xi), 0.5 (1 - y/xi)
-    int iord[QCAP];
-    unsigned char live[168];             // compacted list of live task ids
-};
 
 #ifdef TKB_K2_STATS
 __device__ unsigned long long g_k2stats[24];
-#define K2_T0() long long t0_ = clock64()
-#define K2_ACC(slot) do { if (lane == 0) atomicAdd(&g_k2stats[slot], (unsigned long long)(clock64() - t0_)); t0_ = clock64(); } while (0)
-#define K2_CNT(slot, v) do { if (lane == 0) atomicAdd(&g_k2stats[slot], (unsigned long long)(v)); } while (0)
-#else
-#define K2_T0()
-#define K2_ACC(slot)
-#define K2_CNT(slot, v)
 #endif
 
 template <typename T, int CAP>
@@ -398,8 +373,6 @@ struct SpillList {                       // 1-based list, head (indices < CAP) i
         for (; t <= hi; t++) g[t - 1] = g[t];
     }
 };
-using DList = SpillList<double, QCAP>;
-using IList = SpillList<int, QCAP>;
 
 // integration.f90:616-729
 template <typename DL, typename IL>
@@ -643,373 +616,11 @@ static __device__ __noinline__ void qk21_reduce(const double* fv, double a, doub
         abserr = fmax2((eps_() * 5.0e+01) * resabs, abserr);
 }
 
-// Per-node arguments of a step: sh.ny[node] = (0.5 (1 + y/xi), 0.5 (1 - y/xi)) for the 21 nodes of each
-// of the `nint` intervals (kernels_nlo.f90:52-55 applied to the integration variable).
-TKB_DEV void fill_nodes(QagsShared& sh, double xi, int nint, double a1, double b1, double a2, double b2, int lane)
-{
-    for (int node = lane; node < 21 * nint; node += 32) {
-        const int iv = node / 21, q = node - 21 * iv;
-        const double a = iv ? a2 : a1, b = iv ? b2 : b1;
-        const double centr = 5.0e-01 * (a + b);
-        const double hlgth = 5.0e-01 * (b - a);
-        const double y = node_eta(centr, hlgth, q);
-        const double t = y / xi;
-        sh.ny[node][0] = 0.5 * (1.0 + t);
-        sh.ny[node][1] = 0.5 * (1.0 - t);
-    }
-    __syncwarp();
-}
-
-// task -> the (X, Y, Xo, Yo) of its half kernel.  task = 4*node + 2*dir + half; dir 0 is K(x, y, xi),
-// dir 1 is K(y, x, xi).  (xx1, xx2) = (0.5 (1 + x/xi), 0.5 (1 - x/xi)) of the fixed point x.
-TKB_DEV void task_args(int task, const QagsShared& sh, double xx1, double xx2,
-                       double& X, double& Y, double& Xo, double& Yo)
-{
-    const int node = task >> 2, dir = (task >> 1) & 1, half = task & 1;
-    const double yy1 = sh.ny[node][0], yy2 = sh.ny[node][1];
-    const double U1 = dir ? yy1 : xx1, U2 = dir ? yy2 : xx2;      // first argument's pair
-    const double V1 = dir ? xx1 : yy1, V2 = dir ? xx2 : yy2;      // second argument's pair
-    X = half ? U2 : U1; Y = half ? V2 : V1; Xo = half ? U1 : U2; Yo = half ? V1 : V2;
-}
-
-// Support class of the half kernel at (X, Y): 0 dead (both steps vanish), 1 erbl-only (rho_step == 0,
-// erbl_step != 0), 2 full.  Classes 0 and 1 are only reported when no skipped piece can be non-finite
-// (every denominator / log argument used by any half kernel is non-zero), otherwise 2.
-TKB_DEV int half_class(double X, double Y, double Xo, double Yo)
-{
-    const double Xb = 1.0 - X, Yb = 1.0 - Y;
-    const double r = X / Y;
-    const double omr = 1.0 - r;
-    if (rho_step(r, omr, Y) != 0.0) return 2;
-    const double Xob = 1.0 - Xo, Xbb = 1.0 - Xb;
-    const bool finite = (fabs(X) <= huge_()) && (fabs(Y) <= huge_()) && (fabs(Xo) <= huge_()) && (fabs(Yo) <= huge_());
-    // log|Y/X - 1| must stay finite: |Y - X| > 4 eps |X| guarantees that the rounded quotient differs from 1
-    const bool nz = (X != 0.0) && (Y != 0.0) && (Xb != 0.0) && (Yb != 0.0) && (Xo != 0.0) && (Yo != 0.0) &&
-                    (Xob != 0.0) && (Xbb != 0.0) && (Yo != Xo) && (Yb != Xb) && (Y != Xo) &&
-                    (Yb != Xob) && (Y != Xb) && (Yb != Xbb) && (omr != 0.0) && (r != 0.0) &&
-                    (fabs(Y - X) > 4.0 * eps_() * fabs(X));
-    if (!(finite && nz)) return 2;
-    return (theta_step(X) * theta_step(Xb) != 0.0) ? 1 : 0;
-}
-
-// Warp-cooperative evaluation of the integrand K(x,y,xi) - K(y,x,xi) (kernels_nlo.f90:71-77) at
-// the 21 nodes of `nint` intervals (1 or 2); result in sh.fv.
-template <int KID>
-__device__ __forceinline__ void eval_integrand_warp(double xx1, double xx2, double xi, int nint, double a1, double b1,
-                                                    double a2, double b2, QagsShared& sh, int lane)
-{
-    K2_T0();
-    fill_nodes(sh, xi, nint, a1, b1, a2, b2, lane);
-    const int ntask = 84 * nint;
-    constexpr bool HAS_ERBL = (KID != K_NSN);        // KV1_qq_half_nfl has no ERBL-only piece
-    // classify and compact: full tasks fill sh.live from the front, erbl-only tasks from the back
-    int nfull = 0, nerbl = 0;
-    for (int base = 0; base < ntask; base += 32) {
-        const int task = base + lane;
-        int cls = 0;
-        if (task < ntask) {
-            double X, Y, Xo, Yo;
-            task_args(task, sh, xx1, xx2, X, Y, Xo, Yo);
-            cls = half_class(X, Y, Xo, Yo);
-            if (!HAS_ERBL && cls == 1) cls = 0;
-            if (cls == 0) sh.hv[task] = 0.0;
-        }
-        const unsigned lt = (1u << lane) - 1u;
-        const unsigned mf = __ballot_sync(0xffffffffu, cls == 2);
-        const unsigned me = __ballot_sync(0xffffffffu, cls == 1);
-        if (cls == 2) sh.live[nfull + __popc(mf & lt)] = (unsigned char)task;
-        if (cls == 1) sh.live[167 - (nerbl + __popc(me & lt))] = (unsigned char)task;
-        nfull += __popc(mf);
-        nerbl += __popc(me);
-    }
-    __syncwarp();
-    K2_ACC(0); K2_CNT(8, nfull); K2_CNT(9, nerbl); K2_CNT(10, ntask); K2_CNT(11, (nfull + 31) / 32); K2_CNT(12, (nerbl + 31) / 32);
-    // evaluate the live half kernels, 32 at a time
-    for (int base = 0; base < nfull; base += 32) {
-        const int idx = base + lane;
-        if (idx < nfull) {
-            const int task = sh.live[idx];
-            double X, Y, Xo, Yo;
-            task_args(task, sh, xx1, xx2, X, Y, Xo, Yo);
-            double out[NKERN];
-            eval_half<bit(KID), true>(X, Y, Xo, Yo, out);
-            sh.hv[task] = out[KID];
-        }
-    }
-    __syncwarp();
-    K2_ACC(1);
-    if (HAS_ERBL) {
-        for (int base = 0; base < nerbl; base += 32) {
-            const int idx = base + lane;
-            if (idx < nerbl) {
-                const int task = sh.live[167 - idx];
-                double X, Y, Xo, Yo;
-                task_args(task, sh, xx1, xx2, X, Y, Xo, Yo);
-                double out[NKERN];
-                eval_half<bit(KID), false>(X, Y, Xo, Yo, out);
-                sh.hv[task] = out[KID];
-            }
-        }
-    }
-    __syncwarp();
-    K2_ACC(2);
-    // combine halves and directions
-    for (int node = lane; node < 21 * nint; node += 32) {
-        const double* h = sh.hv + 4 * node;
-        const double Kxy = combine_halves<KID>(h[0], h[1], xi);
-        const double Kyx = combine_halves<KID>(h[2], h[3], xi);
-        sh.fv[node] = Kxy - Kyx;
-    }
-    __syncwarp();
-    K2_ACC(3);
-}
-
-struct QagsOut { double result, abserr; int last, ifail; };
-
-// One QAGS instance on one warp.  Lane 0 owns the scalar state.
-template <int KID>
-__device__ void qags_warp(double x, double xi, double a, double b, QagsShared& sh, QagsScratch* __restrict__ G,
-                          int lane, QagsOut& o)
-{
-    const double epsabs = 1.0e-12, epsrel = 1.0e-06;       // iqags defaults (integration.f90:238-239)
-    const int limit = QLIMIT;
-    bool extrap = false, noext = false;
-    int id, ierro = 0, iroff1 = 0, iroff2 = 0, iroff3 = 0, jupbnd, k, ksgn = 0, ktmin = 0, last = 0, maxerr = 1,
-        nres = 0, nrmax = 1, numrl2 = 2, ifail = 0;
-    double abseps, area = 0, area1, area12, area2, a1 = 0, a2 = 0, b1 = 0, b2 = 0, correc = 0, defabs = 0, defab1, defab2,
-           dres, erlarg = 0, erlast = 0, errbnd, errmax = 0, error1, error2, erro12, errsum = 0, ertest = 0, resabs,
-           reseps, res3la[4], small = 0, result = 0.0, abserr = 0.0;
-    const DList alist{ sh.alist, G->alist }, blist{ sh.blist, G->blist }, rlist{ sh.rlist, G->rlist },
-        elist{ sh.elist, G->elist };
-    const IList iord{ sh.iord, G->iord };
-    double* rlist2 = sh.rlist2;
-    int status = 0;     // lane 0: 0 continue loop, 1 exit loop (Fortran `exit`), 2 goto 115, 3 goto 140 (early return)
-
-    // first approximation
-    const double xx1 = 0.5 * (1.0 + x / xi), xx2 = 0.5 * (1.0 - x / xi);
-    eval_integrand_warp<KID>(xx1, xx2, xi, 1, a, b, a, b, sh, lane);
-    if (lane == 0) {
-        alist[1] = a; blist[1] = b; rlist[1] = 0.0; elist[1] = 0.0;
-        qk21_reduce(sh.fv, a, b, result, abserr, defabs, resabs);
-        dres = fabs(result);
-        errbnd = fmax2(epsabs, epsrel * dres);
-        last = 1;
-        rlist[1] = result;
-        elist[1] = abserr;
-        iord[1] = 1;
-        if (abserr <= 1.0e+02 * eps_() * defabs && abserr > errbnd) ifail = 2;
-        if (limit == 1) ifail = 1;
-        if (ifail != 0 || (abserr <= errbnd && abserr != resabs) || abserr == 0.0) status = 3;
-        else {
-            rlist2[1] = result;
-            errmax = abserr;
-            maxerr = 1;
-            area = result;
-            errsum = abserr;
-            abserr = huge_();
-            if (dres >= (1.0 - 5.0e+01 * eps_()) * defabs) ksgn = 1; else ksgn = -1;
-        }
-    }
-    status = __shfl_sync(0xffffffffu, status, 0);
-
-    if (status != 3) {
-        for (last = 2; last <= limit; last++) {
-            if (lane == 0) {
-                a1 = alist[maxerr];
-                b1 = 5.0e-01 * (alist[maxerr] + blist[maxerr]);
-                a2 = b1;
-                b2 = blist[maxerr];
-                erlast = errmax;
-            }
-            a1 = __shfl_sync(0xffffffffu, a1, 0); b1 = __shfl_sync(0xffffffffu, b1, 0);
-            a2 = __shfl_sync(0xffffffffu, a2, 0); b2 = __shfl_sync(0xffffffffu, b2, 0);
-            eval_integrand_warp<KID>(xx1, xx2, xi, 2, a1, b1, a2, b2, sh, lane);
-            K2_T0();
-            // the two qk21 reductions run side by side on lanes 0 and 1
-            {
-                double r_ = 0, e_ = 0, ra_ = 0, rc_ = 0;
-                if (lane < 2) qk21_reduce(sh.fv + 21 * lane, lane ? a2 : a1, lane ? b2 : b1, r_, e_, ra_, rc_);
-                area2 = __shfl_sync(0xffffffffu, r_, 1);
-                error2 = __shfl_sync(0xffffffffu, e_, 1);
-                defab2 = __shfl_sync(0xffffffffu, rc_, 1);
-                const double resabs2 = __shfl_sync(0xffffffffu, ra_, 1);
-                area1 = r_; error1 = e_; defab1 = rc_; resabs = resabs2;
-            }
-            if (lane == 0) {
-                status = 0;
-                area12 = area1 + area2;
-                erro12 = error1 + error2;
-                errsum = errsum + erro12 - errmax;
-                area = area + area12 - rlist[maxerr];
-                if (defab1 == error1 || defab2 == error2) goto L15;
-                if (fabs(rlist[maxerr] - area12) > (double)1.0e-05f * fabs(area12) || erro12 < 9.9e-01 * errmax) goto L10;
-                if (extrap) iroff2 = iroff2 + 1; else iroff1 = iroff1 + 1;
-L10:
-                if (last > 10 && erro12 > errmax) iroff3 = iroff3 + 1;
-L15:
-                rlist[maxerr] = area1;
-                rlist[last] = area2;
-                errbnd = fmax2(epsabs, epsrel * fabs(area));
-                if (iroff1 + iroff2 >= 10 || iroff3 >= 20) ifail = 2;
-                if (iroff2 >= 5) ierro = 3;
-                if (last == limit) ifail = 1;
-                if (fmax2(fabs(a1), fabs(b2)) <= (1.0 + 1.0e+03 * eps_()) * (fabs(a2) + 1.0e+03 * tiny_())) ifail = 4;
-                if (error2 <= error1) {
-                    alist[last] = a2;
-                    blist[maxerr] = b1;
-                    blist[last] = b2;
-                    elist[maxerr] = error1;
-                    elist[last] = error2;
-                } else {
-                    alist[maxerr] = a2;
-                    alist[last] = a1;
-                    blist[last] = b1;
-                    rlist[maxerr] = area2;
-                    rlist[last] = area1;
-                    elist[maxerr] = error2;
-                    elist[last] = error1;
-                }
-                qsort_(limit, last, maxerr, errmax, elist, iord, nrmax);
-                if (errsum <= errbnd) { status = 2; goto Lend; }
-                if (ifail != 0) { status = 1; goto Lend; }
-                if (last == 2) goto L80;
-                if (noext) goto Lend;
-                erlarg = erlarg - erlast;
-                if (fabs(b1 - a1) > small) erlarg = erlarg + erro12;
-                if (extrap) goto L40;
-                if (fabs(blist[maxerr] - alist[maxerr]) > small) goto Lend;
-                extrap = true;
-                nrmax = 2;
-L40:
-                if (ierro != 3 && erlarg > ertest) {
-                    id = nrmax;
-                    jupbnd = last;
-                    if (last > (2 + limit / 2)) jupbnd = limit + 3 - last;
-                    for (k = id; k <= jupbnd; k++) {
-                        maxerr = iord[nrmax];
-                        errmax = elist[maxerr];
-                        if (fabs(blist[maxerr] - alist[maxerr]) > small) goto Lend;
-                        nrmax = nrmax + 1;
-                    }
-                }
-                numrl2 = numrl2 + 1;
-                rlist2[numrl2] = area;
-                qextr_(numrl2, rlist2, reseps, abseps, res3la, nres);
-                ktmin = ktmin + 1;
-                if (ktmin > 5 && abserr < 1.0e-03 * errsum) ifail = 5;
-                if (abseps < abserr) {
-                    ktmin = 0;
-                    abserr = abseps;
-                    result = reseps;
-                    correc = erlarg;
-                    ertest = fmax2(epsabs, epsrel * fabs(reseps));
-                    if (abserr <= ertest) { status = 1; goto Lend; }
-                }
-                if (numrl2 == 1) noext = true;
-                if (ifail == 5) { status = 1; goto Lend; }
-                maxerr = iord[1];
-                errmax = elist[maxerr];
-                nrmax = 1;
-                extrap = false;
-                small = small * 5.0e-01;
-                erlarg = errsum;
-                goto Lend;
-L80:
-                small = fabs(b - a) * 3.75e-01;
-                erlarg = errsum;
-                ertest = errbnd;
-                rlist2[2] = area;
-Lend:
-                ;
-            }
-            K2_ACC(4);
-            status = __shfl_sync(0xffffffffu, status, 0);
-            if (status != 0) break;
-        }
-        if (lane == 0) {
-            // integration.f90:579-601
-            if (status == 2) goto L115;
-            if (abserr == huge_()) goto L115;
-            if (ifail + ierro == 0) goto L110;
-            if (ierro == 3) abserr = abserr + correc;
-            if (ifail == 0) ifail = 3;
-            if (result != 0.0 && area != 0.0) goto L105;
-            if (abserr > errsum) goto L115;
-            if (area == 0.0) goto L130;
-            goto L110;
-L105:
-            if (abserr / fabs(result) > errsum / fabs(area)) goto L115;
-L110:
-            if (ksgn == (-1) && fmax2(fabs(result), fabs(area)) <= defabs * 1.0e-02) goto L130;
-            if (1.0e-02 > (result / area) || (result / area) > 1.0e+02 || errsum > fabs(area)) ifail = 6;
-            goto L130;
-L115:
-            result = 0.0;
-            for (k = 1; k <= last; k++) result = result + rlist[k];
-            abserr = errsum;
-L130:
-            if (ifail > 2) ifail = ifail - 1;
-        }
-    }
-    if (lane == 0) {
-        o.result = result;
-        o.abserr = abserr;
-        o.last = last;
-        o.ifail = ifail;
-    }
-    __syncwarp();
-}
-
 }  // namespace tkb
-#include "assemble_cst_batched.cuh"
-#include "assemble_cst_replay.cuh"
+#include "qags_step.cuh"
 #include "assemble_cst_pipe.cuh"
+#include "assemble_cst_queue.cuh"
 namespace tkb {
-
-// One launch per constant c (kernel KID).  instance -> (ixi, i, sub); results go to
-// cst_res[((ixi*n + i)*7 + c)*3 + sub] (same index for last / ifail).  Warps pull instances from a
-// global counter: costs vary by three orders of magnitude between instances.
-constexpr int K2_WARPS = 4;
-
-template <int KID>
-__global__ void __launch_bounds__(K2_WARPS * 32, 4)
-assemble_cst_kernel(int c, int n, int nxi, const double* __restrict__ xi_arr, int grid_type,
-                    QagsScratch* __restrict__ scratch, unsigned long long* __restrict__ counter,
-                    double* __restrict__ cst_res, int* __restrict__ cst_last, int* __restrict__ cst_ifail)
-{
-    __shared__ QagsShared s_state[K2_WARPS];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    QagsScratch* G = scratch + (size_t)blockIdx.x * K2_WARPS + warp;
-    QagsShared& sh = s_state[warp];
-    const unsigned long long total = (unsigned long long)nxi * n * 3ULL;
-    for (;;) {
-        unsigned long long inst = 0;
-        if (lane == 0) inst = atomicAdd(counter, 1ULL);
-        inst = __shfl_sync(0xffffffffu, inst, 0);
-        if (inst >= total) break;
-        const int sub = (int)(inst % 3ULL);
-        const unsigned long long row = inst / 3ULL;
-        const int i = (int)(row % (unsigned long long)n) + 1;
-        const int ixi = (int)(row / (unsigned long long)n);
-        const double xi = xi_arr[ixi];
-        const double x = grid_node(i, n, xi, grid_type);
-        // adaptive_integrate's three sub-intervals (integration.f90:56-63)
-        const double eps = 1e-15;
-        const double ymin = -1.0 + eps, ymax = 1.0 - eps;
-        double a, b;
-        if (sub == 0) { a = ymin; b = -fabs(x) - eps; }
-        else if (sub == 1) { a = -fabs(x) + eps; b = fabs(x) - eps; }
-        else { a = fabs(x) + eps; b = ymax; }
-        QagsOut o;
-        qags_warp<KID>(x, xi, a, b, sh, G, lane, o);
-        if (lane == 0) {
-            const size_t idx = ((size_t)row * 7 + (size_t)c) * 3 + (size_t)sub;
-            cst_res[idx] = o.result;
-            cst_last[idx] = o.last;
-            cst_ifail[idx] = o.ifail;
-        }
-    }
-}
 
 // ---------------------------------------------------------------------------------------
 // K3: composition of the nfl slice (matevo.f90:293, 331-335, 370-376, 389-396, 437-446, 463-472).
@@ -1234,113 +845,22 @@ int launch_assemble_fixed(int n, int nxi, const double* xi_dev, int grid_type, d
     return 0;
 }
 
-int launch_assemble_cst(int n, int nxi, const double* xi_dev, int grid_type, void* scratch, int nblocks,
-                        unsigned long long* counters /*[7]*/, double* cst_res, int* cst_last, int* cst_ifail, cudaStream_t st)
-{
-    cudaError_t e = cudaMemsetAsync(counters, 0, 7 * sizeof(unsigned long long), st);
-    if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
-    QagsScratch* S = (QagsScratch*)scratch;
-    const int T = K2_WARPS * 32;
-#define TKB_K2(c, KID)                                                                                          \
-    assemble_cst_kernel<KID><<<nblocks, T, 0, st>>>(c, n, nxi, xi_dev, grid_type, S, counters + c, cst_res,      \
-                                                    cst_last, cst_ifail);                                       \
-    TKB_LAUNCH_CHECK();
-    // the expensive, long-tailed constants first
-    TKB_K2(3, K_V1GG) TKB_K2(4, K_A1GG) TKB_K2(0, K_NSP) TKB_K2(1, K_NSM)
-    TKB_K2(5, K_V1GGN) TKB_K2(6, K_A1GGN) TKB_K2(2, K_NSN)
-#undef TKB_K2
-#ifdef TKB_K2_STATS
-    {
-        cudaStreamSynchronize(st);
-        unsigned long long h[16];
-        cudaMemcpyFromSymbol(h, g_k2stats, sizeof h);
-        fprintf(stderr, "K2 stats (lane-0 cycles): classify %llu full-eval %llu erbl-eval %llu combine %llu bookkeeping %llu | tasks: full %llu erbl %llu total %llu | passes: full %llu erbl %llu\n",
-                h[0], h[1], h[2], h[3], h[4], h[8], h[9], h[10], h[11], h[12]);
-        unsigned long long z[16] = { 0 };
-        cudaMemcpyToSymbol(g_k2stats, z, sizeof z);
-    }
+// ---- K2 launchers.  One launch per constant on its own stream, so that a draining launch does not hold up the next.
+#ifndef TKB_QQG
+#define TKB_QQG 16
 #endif
-    return 0;
-}
-int assemble_cst_warps_per_block() { return K2_WARPS; }
-
-// batched form: one persistent block per SM, QB instances advanced in lock-step rounds
-int launch_assemble_cst_batched(int n, int nxi, const double* xi_dev, int grid_type, void* lists, int nblocks,
-                                unsigned long long* counters /*[7]*/, double* cst_res, int* cst_last, int* cst_ifail,
-                                cudaStream_t st, cudaStream_t* side /*[7] or null*/, cudaEvent_t fork, cudaEvent_t* join)
-{
-    cudaError_t e = cudaMemsetAsync(counters, 0, 7 * sizeof(unsigned long long), st);
-    if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
-    if (side) {
-        // every constant runs on its own stream so that a draining launch does not hold up the next one
-        e = cudaEventRecord(fork, st);
-        if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
-        for (int k = 0; k < 7; k++) {
-            e = cudaStreamWaitEvent(side[k], fork, 0);
-            if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
-        }
-    }
-    const size_t smem = sizeof(QBatchShared);
-#define TKB_K2B(c, KID)                                                                                              \
-    e = cudaFuncSetAttribute(assemble_cst_batched_kernel<KID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    if (e != cudaSuccess) return set_error(cudaGetErrorString(e));                                                   \
-    assemble_cst_batched_kernel<KID><<<nblocks, QT, smem, side ? side[c] : st>>>(                                     \
-        c, n, nxi, xi_dev, grid_type, (QLists*)lists + (size_t)(side ? c : 0) * nblocks * QB, counters + c, cst_res,  \
-        cst_last, cst_ifail);                                                                                        \
-    TKB_LAUNCH_CHECK();
-    TKB_K2B(3, K_V1GG) TKB_K2B(4, K_A1GG) TKB_K2B(0, K_NSP) TKB_K2B(1, K_NSM)
-    TKB_K2B(5, K_V1GGN) TKB_K2B(6, K_A1GGN) TKB_K2B(2, K_NSN)
-#undef TKB_K2B
-    if (side) {
-        for (int k = 0; k < 7; k++) {
-            e = cudaEventRecord(join[k], side[k]);
-            if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
-            e = cudaStreamWaitEvent(st, join[k], 0);
-            if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
-        }
-    }
-#ifdef TKB_K2_STATS
-    {
-        cudaStreamSynchronize(st);
-        unsigned long long h[16];
-        cudaMemcpyFromSymbol(h, g_k2stats, sizeof h);
-        fprintf(stderr, "K2 batched stats (thread-0 cycles summed over blocks): S %llu N %llu C %llu E %llu K %llu | rounds %llu active-slot-rounds %llu (fill %.2f)\n",
-                h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[5] ? (double)h[6] / ((double)QB * h[5]) : 0.0);
-        unsigned long long z[16] = { 0 };
-        cudaMemcpyToSymbol(g_k2stats, z, sizeof z);
-    }
+#ifndef TKB_QQN
+#define TKB_QQN 2
 #endif
-    return 0;
-}
-// leader / follower form (assemble_cst_replay.cuh).  Streams: side[0] GG leader, side[1] NS leader,
-// side[2..6] followers (KA1_GG, KV1_GG_nfl, KA1_GG_nfl after the GG leader; KV1_NSm, KV1_NS_nfl after the NS leader).
-#ifndef TKB_RP_SLOTS
-#define TKB_RP_SLOTS 16
+#ifndef TKB_QQT
+#define TKB_QQT 768
 #endif
-constexpr int RP_SLOTS = TKB_RP_SLOTS;             // slots per block reserved in the global list area (max over the launches)
-size_t qags_replay_lists_bytes(int nblocks) { return sizeof(QLists) * (size_t)RP_SLOTS * nblocks * 7; }
-size_t qags_replay_log_doubles(int which /*0 NS pair log, 1 unused*/, size_t ninst, int L) { return which == 0 ? ninst * (size_t)L * (4 + 42) : 0; }
-
-template <int KID, int C1, int C2, int C3, bool FOLLOW, int QBv, int QTv>
-static int launch_replay_one(int c, int n, int nxi, const double* xi_dev, int grid_type, QLists* lists, int sms,
-                             unsigned long long* counter, double* cst_res, int* cst_last, int* cst_ifail, double* log,
-                             int* nlog, int L, int rec, int ci, cudaStream_t st)
-{
-    using KS = KernelSet<KID, C1, C2, C3>;
-    const size_t smem = sizeof(QReplayShared<QBv, KS::NKER>);
-    auto kern = assemble_cst_replay_kernel<KID, C1, C2, C3, FOLLOW, QBv, QTv, 2>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
-    const unsigned long long total = (unsigned long long)nxi * n * 3ULL;
-    long long nb = (long long)sms * 2;
-    const long long want = (long long)((total + QBv - 1) / QBv);
-    if (nb > want) nb = want;
-    kern<<<(int)nb, QTv, smem, st>>>(c, n, nxi, xi_dev, grid_type, lists, counter, cst_res, cst_last, cst_ifail, log, nlog,
-                                     L, rec, ci);
-    TKB_LAUNCH_CHECK();
-    return 0;
-}
-
+#ifndef TKB_QQG_L
+#define TKB_QQG_L TKB_QQG
+#endif
+#ifndef TKB_QQN_L
+#define TKB_QQN_L TKB_QQN
+#endif
 #ifndef TKB_QPG
 #define TKB_QPG 16
 #endif
@@ -1363,7 +883,6 @@ static int launch_pipe_one(int c, int n, int nxi, const double* xi_dev, int grid
     constexpr int QG = TKB_QPG, NT = TKB_QPT, BPS = TKB_QPBPS;
     // bookkeeping warps per group: the cheap nfl kernels are bookkeeping-bound
     constexpr int BWG = (KID == K_NSN || KID == K_V1GGN || KID == K_A1GGN) ? TKB_QPBWG_NFL : TKB_QPBWG;
-    static_assert(2 * QG * BPS <= RP_SLOTS * 2, "global list area reserved per SM");
     const size_t smem = sizeof(QPipeShared<QG>);
     auto kern = assemble_cst_pipe_kernel<KID, QG, NT, BPS, BWG>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1392,11 +911,54 @@ static int launch_pipe_one(int c, int n, int nxi, const double* xi_dev, int grid
     return 0;
 }
 
-int launch_assemble_cst_replay(int n, int nxi, const double* xi_dev, int grid_type, void* lists, int sms,
-                               unsigned long long* counters /*[7]*/, double* cst_res, int* cst_last, int* cst_ifail,
-                               double* log_ns, double* log_gg, int* nlog_ns, int* nlog_gg, int L,
-                               cudaStream_t st, cudaStream_t* side /*[7]*/, cudaEvent_t fork, cudaEvent_t* join /*[7]*/,
-                               cudaEvent_t* leader_done /*[2]*/)
+template <int KID>
+static int launch_queue_one(int c, int n, int nxi, const double* xi_dev, int grid_type, QLists* lists, int sms,
+                            unsigned long long* counter, double* cst_res, int* cst_last, int* cst_ifail, cudaStream_t st)
+{
+    constexpr bool LIGHT = (KID == K_NSN || KID == K_V1GGN || KID == K_A1GGN);
+    constexpr int QG = LIGHT ? TKB_QQG_L : TKB_QQG, NG = LIGHT ? TKB_QQN_L : TKB_QQN, NT = TKB_QQT;
+    const size_t smem = sizeof(QQueueShared<QG, NG>);
+    auto kern = assemble_cst_queue_kernel<KID, QG, NG, NT>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
+    const unsigned long long total = (unsigned long long)nxi * n * 3ULL;
+    long long nb = (long long)sms;
+    const long long want = (long long)((total + QG * NG - 1) / (QG * NG));
+    if (nb > want) nb = want;
+    kern<<<(int)nb, NT, smem, st>>>(c, n, nxi, xi_dev, grid_type, lists, counter, cst_res, cst_last, cst_ifail);
+    TKB_LAUNCH_CHECK();
+#ifdef TKB_K2_STATS
+    {
+        cudaStreamSynchronize(st);
+        unsigned long long h[24];
+        cudaMemcpyFromSymbol(h, g_k2stats, sizeof h);
+        const double wl = (double)h[7];            // summed worker-warp lifetimes
+        fprintf(stderr, "K2 queue KID %d: worker time: NODE %.1f %% EVAL %.1f %% K %.1f %% idle(sleep) %.1f %% other %.1f %% | %llu chunks, %.0f cyc/chunk | bookkeeper per round: wait %.0f, work %.0f cyc (%llu rounds)\n",
+                KID, 100. * h[16] / wl, 100. * h[17] / wl, 100. * h[18] / wl, 100. * h[4] / wl,
+                100. * (wl - h[16] - h[17] - h[18] - h[4]) / wl, h[19], h[19] ? (double)(h[16] + h[17] + h[18]) / h[19] : 0.,
+                h[3] ? (double)h[0] / h[3] : 0., h[3] ? (double)h[1] / h[3] : 0., h[3]);
+        fprintf(stderr, "   bookkeeping detail: qk21 sums %.0f cyc per round | qsort %.0f cyc x %llu calls (%.1f per round) | qextr %.0f cyc x %llu calls (%.2f per round)\n",
+                h[3] ? (double)h[12] / h[3] : 0., h[9] ? (double)h[8] / h[9] : 0., h[9], h[3] ? (double)h[9] / h[3] : 0.,
+                h[11] ? (double)h[10] / h[11] : 0., h[11], h[3] ? (double)h[11] / h[3] : 0.);
+        unsigned long long z[24] = { 0 };
+        cudaMemcpyToSymbol(g_k2stats, z, sizeof z);
+    }
+#endif
+    return 0;
+}
+
+// list slots reserved per SM and constant in the global spill area
+constexpr int K2_SLOTS = (2 * TKB_QPG * TKB_QPBPS > TKB_QQG * TKB_QQN)
+                             ? ((2 * TKB_QPG * TKB_QPBPS > TKB_QQG_L * TKB_QQN_L) ? 2 * TKB_QPG * TKB_QPBPS : TKB_QQG_L * TKB_QQN_L)
+                             : ((TKB_QQG * TKB_QQN > TKB_QQG_L * TKB_QQN_L) ? TKB_QQG * TKB_QQN : TKB_QQG_L * TKB_QQN_L);
+size_t qags_lists_bytes(int sms) { return sizeof(QLists) * (size_t)K2_SLOTS * (size_t)sms * 7; }
+
+// All seven constants: instance -> (ixi, i, sub); results go to cst_res[((ixi*n + i)*7 + c)*3 + sub] (same index for
+// last / ifail).  Blocks pull instances from one global counter per constant: costs vary by three orders of magnitude
+// between instances.  queue = the work-queue form (TKB_K2_MODE=queue), else the role-split pipeline.
+int launch_assemble_cst(int n, int nxi, const double* xi_dev, int grid_type, void* lists, int sms, int queue,
+                        unsigned long long* counters /*[7]*/, double* cst_res, int* cst_last, int* cst_ifail,
+                        cudaStream_t st, cudaStream_t* side /*[7]*/, cudaEvent_t fork, cudaEvent_t* join /*[7]*/)
 {
     cudaError_t e = cudaMemsetAsync(counters, 0, 7 * sizeof(unsigned long long), st);
     if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
@@ -1407,68 +969,29 @@ int launch_assemble_cst_replay(int n, int nxi, const double* xi_dev, int grid_ty
         if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
     }
     QLists* Lp = (QLists*)lists;
-    const size_t region = (size_t)RP_SLOTS * sms * 2;
-    const int rec_ns = 4 + 42 * 2, rec_gg = 4 + 42 * 3;
-#define RP_ARGS(c) c, n, nxi, xi_dev, grid_type, Lp + region * (c), sms, counters + (c), cst_res, cst_last, cst_ifail
-    // Sharing (TKB_K2_MODE=share|replay) paid in the lock-step form only where the follower's evaluation saving
-    // exceeded its (unchanged) bookkeeping cost and the leader's extra work: KV1_NSm behind KV1_NSp (-19 ms / +4 ms
-    // on C3); the gluon family and the cheap nfl kernels are bookkeeping-bound as followers.
-    const int rec_pair = 4 + 42;
-    // role-split pipeline (assemble_cst_pipe.cuh) unless TKB_K2_MODE=replay asks for the lock-step form
-    const char* mode_ = getenv("TKB_K2_MODE");
-    const bool pipe = !(mode_ && mode_[0] == 'r');
-#define RP_PLAIN(c, KID, strm)                                                                                        \
-    if (pipe ? launch_pipe_one<KID>(RP_ARGS(c), strm)                                                                  \
-             : launch_replay_one<KID, -1, -1, -1, false, 16, 384>(RP_ARGS(c), nullptr, nullptr, 0, 0, 0, strm)) return 1;
-    // KV1_NSp / KV1_NSm as leader / follower (assemble_cst_replay.cuh) only on request: with the pipeline and the
-    // per-instance tables two unshared launches are faster (C3: K2 150 ms against 160 ms)
-    const bool share_ns = (mode_ && (mode_[0] == 's' || mode_[0] == 'r'));
-    RP_PLAIN(3, K_V1GG, side[0])
-    if (share_ns) {
-        if (launch_replay_one<K_NSP, K_NSM, -1, -1, false, 14, 352>(RP_ARGS(0), log_ns, nlog_ns, L, rec_pair, 0, side[1])) return 1;
-        e = cudaEventRecord(leader_done[0], side[1]);
-        if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
-    } else {
-        RP_PLAIN(0, K_NSP, side[1])
-    }
-    RP_PLAIN(4, K_A1GG, side[2])
-    if (share_ns) {
-        e = cudaStreamWaitEvent(side[5], leader_done[0], 0);
-        if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
-        if (launch_replay_one<K_NSM, -1, -1, -1, true, 16, 384>(RP_ARGS(1), log_ns, nlog_ns, L, rec_pair, 0, side[5])) return 1;
-    } else {
-        RP_PLAIN(1, K_NSM, side[5])
-    }
-    RP_PLAIN(5, K_V1GGN, side[3])
-    RP_PLAIN(6, K_A1GGN, side[4])
-    RP_PLAIN(2, K_NSN, side[6])
-#undef RP_PLAIN
-    (void)log_gg; (void)nlog_gg; (void)rec_ns; (void)rec_gg; (void)leader_done;
-#undef RP_ARGS
+    const size_t region = (size_t)K2_SLOTS * sms;
+#define K2_ONE(c, KID, strm)                                                                                           \
+    if (queue ? launch_queue_one<KID>(c, n, nxi, xi_dev, grid_type, Lp + region * (c), sms, counters + (c), cst_res,   \
+                                      cst_last, cst_ifail, strm)                                                       \
+              : launch_pipe_one<KID>(c, n, nxi, xi_dev, grid_type, Lp + region * (c), sms, counters + (c), cst_res,    \
+                                     cst_last, cst_ifail, strm)) return 1;
+    // the expensive, long-tailed constants first
+    K2_ONE(3, K_V1GG, side[0])
+    K2_ONE(0, K_NSP, side[1])
+    K2_ONE(4, K_A1GG, side[2])
+    K2_ONE(1, K_NSM, side[5])
+    K2_ONE(5, K_V1GGN, side[3])
+    K2_ONE(6, K_A1GGN, side[4])
+    K2_ONE(2, K_NSN, side[6])
+#undef K2_ONE
     for (int k = 0; k < 7; k++) {
         e = cudaEventRecord(join[k], side[k]);
         if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
         e = cudaStreamWaitEvent(st, join[k], 0);
         if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
     }
-#ifdef TKB_K2_STATS
-    {
-        cudaStreamSynchronize(st);
-        unsigned long long h[16];
-        cudaMemcpyFromSymbol(h, g_k2stats, sizeof h);
-        fprintf(stderr, "K2 S-phase stats: qsort %.0f cyc x %llu | qextr %.0f cyc x %llu | qk21_reduce %.0f cyc | qags_step (incl. qsort/qextr) %.0f cyc x %llu\n",
-                h[9] ? (double)h[8] / h[9] : 0.0, h[9], h[11] ? (double)h[10] / h[11] : 0.0, h[11],
-                h[14] ? (double)h[12] / h[14] : 0.0, h[14] ? (double)h[13] / h[14] : 0.0, h[14]);
-        unsigned long long z[16] = { 0 };
-        cudaMemcpyToSymbol(g_k2stats, z, sizeof z);
-    }
-#endif
     return 0;
 }
-
-size_t qags_batched_bytes_per_block() { return qags_lists_bytes(); }
-int qags_batched_instances_per_block() { return QB; }
-int qags_batched_blocks_per_sm() { return QBLOCKS_PER_SM; }
 
 int launch_compose(int n, int nxi, int nfl, const double* P, const double* diag, const double* cst_res,
                    double* NS0, double* NS1p, double* NS1m, double* SGV0, double* SGA0, double* SGV1, double* SGA1,

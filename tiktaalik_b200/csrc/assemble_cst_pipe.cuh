@@ -1,7 +1,7 @@
 // assemble_cst_pipe.cuh -- K2 with the QUADPACK bookkeeping taken off the evaluators' critical path.
-// Included by assemble.cu after assemble_cst_batched.cuh (whose QSlot / QHead / qags_* helpers it reuses).
+// Included by assemble.cu after qags_step.cuh (QSlot / QHead / qags_first / qags_step).
 //
-// In the lock-step form (assemble_cst_batched.cuh) every round ends in a bookkeeping phase in which one
+// In the lock-step form of round 1 (removed) every round ends in a bookkeeping phase in which one
 // lane pair per instance runs QUADPACK's scalar code (qk21 sums, list update, qsort, epsilon table: about
 // 15-25 k cycles of dependent FP64 latency, the maximum over the block's instances) while all other threads
 // wait at the barrier: ncu showed 4.1 of 11.9 warp-cycles per issued instruction spent in barrier stalls.
@@ -32,10 +32,6 @@ struct QPipeShared {
     int next[2];                        // E phase: next 32-task chunk of the group
     long long t_exh;                    // TKB_K2_STATS: clock at which this block first found the queue empty
     int act[2][8];                      // per group and bookkeeping warp: it still has a running instance
-#ifdef TKB_QP_STEAL
-    int req_round[2];                   // per group: number of request sets its bookkeeper has posted
-    int nslice[2];                      // per group: next 32-node slice of the node pass
-#endif
 };
 
 // which entries of the per-instance table (PRE_*) the half kernel of one constant reads (the N_* flags of eval_half)
@@ -82,74 +78,6 @@ __device__ __forceinline__ void qp_bar_arrive(int id, int count)
     }
 }
 
-#ifdef TKB_QP_STEAL
-// EXPERIMENT (DESIGN.md section 10 b; compiled only with -DTKB_QP_STEAL): the node pass of group g in 32-node
-// slices drawn from a counter, so that warps which run out of evaluation chunks of the OTHER group can do slices
-// as soon as g's requests are posted instead of idling at the barrier.  Same per-node arithmetic as the in-line pass.
-template <int KID, int QG>
-static __device__ __noinline__ void qp_node_slices(QPipeShared<QG>& sh, int g, int lane)
-{
-    constexpr bool HAS_ERBL = (KID != K_NSN);
-    constexpr int NSL = (QG * 42 + 31) / 32;
-    for (;;) {
-        int k = 0;
-        if (lane == 0) k = atomicAdd(&sh.nslice[g], 1);
-        k = __shfl_sync(0xffffffffu, k, 0);
-        if (k >= NSL) break;
-        const int e = 32 * k + lane;
-        const bool inr = e < QG * 42;
-        const int s = g * QG + (inr ? e / 42 : 0), node = inr ? e % 42 : 0;
-        const QSlot& S = sh.slot[s];
-        const bool act = inr && node < 21 * S.nint;
-        int cls[4] = { 0, 0, 0, 0 };
-        if (act) {
-            const int iv = node / 21, q = node - 21 * iv;
-            const double a = iv ? S.a2 : S.a1, b = iv ? S.b2 : S.b1;
-            const double centr = 5.0e-01 * (a + b);
-            const double hlgth = 5.0e-01 * (b - a);
-            const double y = node_eta(centr, hlgth, q);
-            const double t = y / S.xi;
-            const double yy1 = 0.5 * (1.0 + t), yy2 = 0.5 * (1.0 - t);
-            sh.ny[s][node][0] = yy1;
-            sh.ny[s][node][1] = yy2;
-            const double xx1 = S.xx1, xx2 = S.xx2;
-            const bool safe = node_is_safe(xx1, xx2, yy1, yy2);
-            cls[0] = task_class(xx1, yy1, safe);
-            cls[1] = task_class(xx2, yy2, safe);
-            cls[2] = task_class(yy1, xx1, safe);
-            cls[3] = task_class(yy2, xx2, safe);
-#pragma unroll
-            for (int c4 = 0; c4 < 4; c4++) {
-                if (!HAS_ERBL && cls[c4] == 1) cls[c4] = 0;
-                if (cls[c4] == 0) sh.hv[s][4 * node + c4] = 0.0;
-            }
-        }
-        const unsigned lt = (1u << lane) - 1u;
-#pragma unroll
-        for (int d = 0; d < 2; d++) {
-            const unsigned f0 = __ballot_sync(0xffffffffu, cls[2 * d] == 2), f1 = __ballot_sync(0xffffffffu, cls[2 * d + 1] == 2);
-            const unsigned r0 = HAS_ERBL ? __ballot_sync(0xffffffffu, cls[2 * d] == 1) : 0u;
-            const unsigned r1 = HAS_ERBL ? __ballot_sync(0xffffffffu, cls[2 * d + 1] == 1) : 0u;
-            const int nf = __popc(f0) + __popc(f1), ne = __popc(r0) + __popc(r1);
-            int bf = 0, be = 0;
-            if (lane == 0) {
-                if (nf) bf = atomicAdd(&sh.nfull[g][d], nf);
-                if (ne) be = atomicAdd(&sh.nerbl[g][d], ne);
-            }
-            bf = __shfl_sync(0xffffffffu, bf, 0);
-            be = __shfl_sync(0xffffffffu, be, 0);
-            const unsigned short id0 = (unsigned short)((s - g * QG) * 168 + 4 * node + 2 * d);
-            if (cls[2 * d] == 2) sh.live[g][d][bf + __popc(f0 & lt)] = id0;
-            if (cls[2 * d + 1] == 2) sh.live[g][d][bf + __popc(f0) + __popc(f1 & lt)] = id0 + 1;
-            if (HAS_ERBL) {
-                if (cls[2 * d] == 1) sh.live[g][d][QG * 84 - 1 - (be + __popc(r0 & lt))] = id0;
-                if (cls[2 * d + 1] == 1) sh.live[g][d][QG * 84 - 1 - (be + __popc(r0) + __popc(r1 & lt))] = id0 + 1;
-            }
-        }
-    }
-}
-#endif
-
 template <int KID, int QG, int NT, int BPS, int BWG>
 __global__ void __launch_bounds__(NT, BPS)
 assemble_cst_pipe_kernel(int c, int n, int nxi, const double* __restrict__ xi_arr, int grid_type,
@@ -167,10 +95,6 @@ assemble_cst_pipe_kernel(int c, int n, int nxi, const double* __restrict__ xi_ar
     const unsigned long long total = (unsigned long long)nxi * n * 3ULL;
     if (tid < 2 * QG) sh.slot[tid].nint = 0;
     if (tid == 0) sh.t_exh = 0;
-#ifdef TKB_QP_STEAL
-    static_assert(BWG == 1, "TKB_QP_STEAL: one bookkeeping warp per group");
-    if (tid < 2) { sh.req_round[tid] = 0; sh.nslice[tid] = 0; }
-#endif
     if (tid < 2) { sh.nfull[tid][0] = sh.nfull[tid][1] = 0; sh.nerbl[tid][0] = sh.nerbl[tid][1] = 0; sh.next[tid] = 0; }
     __syncthreads();
 
@@ -256,17 +180,10 @@ assemble_cst_pipe_kernel(int c, int n, int nxi, const double* __restrict__ xi_ar
                     sh.nfull[g][0] = sh.nfull[g][1] = 0;
                     sh.nerbl[g][0] = sh.nerbl[g][1] = 0;
                     sh.next[g] = 0;
-#ifdef TKB_QP_STEAL
-                    sh.nslice[g] = 0;
-#endif
                 }
                 sh.act[g][bw] = (act != 0u) ? 1 : 0;
             }
             __syncwarp();
-#ifdef TKB_QP_STEAL
-            __threadfence_block();                                   // slot data, counters and act[] before the flag
-            if (lane == 0) *(volatile int*)&sh.req_round[g] = round + 1;
-#endif
             // the group's bookkeepers and the evaluators meet here; all of them then read the same act[] flags
             // (rewritten only after the next VAL barrier, which needs every reader's arrival)
 #ifdef TKB_K2_STATS
@@ -295,9 +212,6 @@ assemble_cst_pipe_kernel(int c, int n, int nxi, const double* __restrict__ xi_ar
     const long long tk0_ = clock64();
 #endif
     int alive = 3;
-#ifdef TKB_QP_STEAL
-    int rnd0 = 0, rnd1 = 0;             // request sets of group 0 / 1 that the evaluators have taken
-#endif
     for (int g = 0; alive != 0; g ^= 1) {
         if (!((alive >> g) & 1)) continue;
 #ifdef TKB_K2_STATS
@@ -313,15 +227,9 @@ assemble_cst_pipe_kernel(int c, int n, int nxi, const double* __restrict__ xi_ar
             for (int b = 0; b < BWG; b++) any |= *(volatile int*)&sh.act[g][b];
             if (!any) { alive &= ~(1 << g); continue; }
         }
-#ifdef TKB_QP_STEAL
-        if (g) rnd1++; else rnd0++;
-#endif
-        // ---- N + C: node arguments, support classes, compaction (see assemble_cst_batched.cuh); the tasks are
+        // ---- N + C: node arguments, support classes, compaction; the tasks are
         // listed per direction so that a warp evaluates one direction (one set of pre-computed values) ----
         // (warp-aggregated compaction: one shared-memory atomic per warp and list instead of one per thread)
-#ifdef TKB_QP_STEAL
-        qp_node_slices<KID, QG>(sh, g, etid & 31);                  // whatever slices were not taken during the other group's E
-#else
         for (int e0 = 0; e0 < QG * 42; e0 += NE) {
             const int e = e0 + etid;
             const bool inr = e < QG * 42;
@@ -375,7 +283,6 @@ assemble_cst_pipe_kernel(int c, int n, int nxi, const double* __restrict__ xi_ar
                 }
             }
         }
-#endif
         // one-argument transcendental values of the instances that start in this round (nint == 1)
         if (qp_pre_need<KID>() != 0u) {
             for (int e = etid; e < QG * 2 * PRE_N; e += NE) {
@@ -425,24 +332,6 @@ assemble_cst_pipe_kernel(int c, int n, int nxi, const double* __restrict__ xi_ar
                 else eval_half<bit(KID), false, 3>(X, Y, Xo, Yo, out, preS, preO, dir ? 2 : 1);
                 sh.hv[s][task] = out[KID];
             }
-#ifdef TKB_QP_STEAL
-            // out of chunks: if the other group's next requests are already posted, start its node pass
-            {
-                const int go = g ^ 1;
-                if ((alive >> go) & 1) {
-                    int ready = 0;
-                    if (elane == 0) {
-                        ready = (*(volatile int*)&sh.req_round[go] == (go ? rnd1 : rnd0) + 1) ? 1 : 0;
-                        if (ready) ready = *(volatile int*)&sh.act[go][0];
-                    }
-                    ready = __shfl_sync(0xffffffffu, ready, 0);
-                    if (ready) {
-                        __threadfence_block();
-                        qp_node_slices<KID, QG>(sh, go, elane);
-                    }
-                }
-            }
-#endif
         }
         qp_bar_sync(QP_BAR_EV, NE);
 #ifdef TKB_K2_STATS

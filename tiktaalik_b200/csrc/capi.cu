@@ -10,6 +10,7 @@
 #include <string>
 #include <vector>
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include "../../include/tiktaalik_b200.h"
 #include "tkb_internal.h"
 
@@ -23,6 +24,10 @@ int set_error(const char* msg)
     g_err = msg ? msg : "unknown error";
     return 1;
 }
+
+// NVTX v3 is header-only: the calls are no-ops unless a profiler injects itself (nsys, ncu --nvtx)
+void nvtx_push(const char* name) { nvtxRangePushA(name); }
+void nvtx_pop() { nvtxRangePop(); }
 
 #define CUDA_OK(call)                                                                  \
     do {                                                                               \
@@ -61,9 +66,6 @@ struct Context {
     cudaEvent_t ev[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
     bool ev_k = false, ev_m = false;
     cudaStream_t side[7] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
-    cudaEvent_t leader_done[2] = { nullptr, nullptr };
-    double* qlog = nullptr;     // leader logs (NS then GG) + step counts, kept across calls
-    size_t qlog_bytes = 0;
     cudaStream_t k1_stream = nullptr;
     cudaEvent_t k1_fork = nullptr, k1_done = nullptr;
     bool k1_overlapped = false;
@@ -114,8 +116,6 @@ static int ensure_events()
         CUDA_OK(cudaEventCreateWithFlags(&g.k1_fork, cudaEventDisableTiming));
         CUDA_OK(cudaEventCreate(&g.k1_done));
         CUDA_OK(cudaEventCreateWithFlags(&g.fork, cudaEventDisableTiming));
-        CUDA_OK(cudaEventCreateWithFlags(&g.leader_done[0], cudaEventDisableTiming));
-        CUDA_OK(cudaEventCreateWithFlags(&g.leader_done[1], cudaEventDisableTiming));
         for (int k = 0; k < 7; k++) {
             CUDA_OK(cudaStreamCreateWithFlags(&g.side[k], cudaStreamNonBlocking));
             CUDA_OK(cudaEventCreateWithFlags(&g.join[k], cudaEventDisableTiming));
@@ -163,99 +163,41 @@ static int make_kernels_impl(int nx, int nxi, const double* xi_host, int grid_ty
     if (launch_pre_table(nx, nxi, g.d_xi, grid_type, g.pre_tab, st)) return 1;
     CUDA_OK(cudaEventRecord(g.ev[0], st));
     if (!overlap_k1) {
-        if (launch_assemble_fixed(nx, nxi, g.d_xi, grid_type, g.P, g.diag, st)) return 1;
+        nvtx_push("tkb K1 fixed quadrature");
+        const int rc1 = launch_assemble_fixed(nx, nxi, g.d_xi, grid_type, g.P, g.diag, st);
+        nvtx_pop();
+        if (rc1) return 1;
     }
     CUDA_OK(cudaEventRecord(g.ev[1], st));
 
-    // QAGS: persistent blocks pulling instances from a counter
+    // QAGS: one persistent block per SM and constant pulling instances from a counter (assemble.cu).  Form: the
+    // role-split pipeline (default) or the work queue (TKB_K2_MODE=queue, kept for comparison)
     int dev = 0, sms = 148;
     CUDA_OK(cudaGetDevice(&dev));
     CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const unsigned long long total = (unsigned long long)rows * 3ULL;       // instances per constant
-    const int wpb = assemble_cst_warps_per_block();
-    long long want = (long long)((total + wpb - 1) / wpb);
-    int nblocks = sms * 8;        // more than fit at once: the spare blocks start as others drain
-    if (const char* env = getenv("TKB_K2_BLOCKS_PER_SM")) { const int v = atoi(env); if (v > 0) nblocks = sms * v; }   // tuning knob
-    if ((long long)nblocks > want) nblocks = (int)want;
-    // K2 form: role-split pipeline, one launch per constant (default).  Kept for comparison behind TKB_K2_MODE:
-    // share (KV1_NSp / KV1_NSm as leader / follower with an evaluation log), replay (lock-step blocks for all,
-    // with that sharing), batched (lock-step, no sharing), warp (one instance per warp)
     const char* mode = getenv("TKB_K2_MODE");
-    const bool warpmode = (mode && mode[0] == 'w');
-    const bool replay = !(mode && (mode[0] == 'w' || mode[0] == 'b'));
-    const bool batched = !warpmode;
-    int rc = 0;
-    if (replay) {
-        const size_t ninst = (size_t)rows * 3;
-        // log depth: as many steps as fit a memory budget (instances with longer paths leave the log there)
-        size_t budget = (size_t)6 << 30;
-        if (const char* env = getenv("TKB_K2_LOG_GB")) budget = (size_t)atof(env) * ((size_t)1 << 30);
-        long long Lmax = (long long)(budget / (8.0 * (double)ninst * 46.0));
-        int L = (int)(Lmax > 48 ? 48 : (Lmax < 4 ? 4 : Lmax));
-        const size_t lists_b = qags_replay_lists_bytes(sms * 2);
-        const size_t need = lists_b + 64;
-        if (g.scratch_bytes < need) {
-            if (g.scratch) cudaFree(g.scratch);
-            g.scratch = nullptr;
-            g.scratch_bytes = 0;
-            CUDA_OK(cudaMalloc(&g.scratch, need));
-            g.scratch_bytes = need;
-        }
-        const bool sharing = (mode && (mode[0] == 's' || mode[0] == 'r'));
-        const size_t dn = sharing ? qags_replay_log_doubles(0, ninst, L) : 0, dg = 0;
-        const size_t lneed = sharing ? dn * sizeof(double) + 2 * ninst * sizeof(int) : 0;
-        if (!sharing && g.qlog) {            // the evaluation log of an earlier sharing run is not needed any more
-            cudaFree(g.qlog);
-            g.qlog = nullptr;
-            g.qlog_bytes = 0;
-        }
-        if (g.qlog_bytes < lneed) {
-            if (g.qlog) cudaFree(g.qlog);
-            g.qlog = nullptr;
-            g.qlog_bytes = 0;
-            CUDA_OK(cudaMalloc(&g.qlog, lneed));
-            g.qlog_bytes = lneed;
-        }
-        int* nl = sharing ? (int*)(g.qlog + dn + dg) : nullptr;
-        rc = launch_assemble_cst_replay(nx, nxi, g.d_xi, grid_type, (char*)g.scratch + 64, sms,
-                                        (unsigned long long*)g.scratch, g.cst_res, g.cst_last, g.cst_ifail,
-                                        g.qlog, g.qlog + dn, nl, nl + ninst, L, st, g.side, g.fork, g.join, g.leader_done);
-    } else
-    if (batched) {
-        const int qb = qags_batched_instances_per_block();
-        int nb = sms * qags_batched_blocks_per_sm();
-        const long long wantb = (long long)((total + qb - 1) / qb);
-        if ((long long)nb > wantb) nb = (int)wantb;
-        const bool multi = !(getenv("TKB_K2_ONE_STREAM"));
-        const size_t need = qags_batched_bytes_per_block() * (size_t)nb * (multi ? 7 : 1) + 64;
-        if (g.scratch_bytes < need) {
-            if (g.scratch) cudaFree(g.scratch);
-            g.scratch = nullptr;
-            g.scratch_bytes = 0;
-            CUDA_OK(cudaMalloc(&g.scratch, need));
-            g.scratch_bytes = need;
-        }
-        rc = launch_assemble_cst_batched(nx, nxi, g.d_xi, grid_type, (char*)g.scratch + 64, nb,
-                                         (unsigned long long*)g.scratch, g.cst_res, g.cst_last, g.cst_ifail, st,
-                                         multi ? g.side : nullptr, g.fork, g.join);
-    } else {
-        const size_t need = qags_scratch_bytes() * (size_t)nblocks * wpb + 64;
-        if (g.scratch_bytes < need) {
-            if (g.scratch) cudaFree(g.scratch);
-            g.scratch = nullptr;
-            g.scratch_bytes = 0;
-            CUDA_OK(cudaMalloc(&g.scratch, need));
-            g.scratch_bytes = need;
-        }
-        unsigned long long* counter = (unsigned long long*)g.scratch;             // 8 counters, then the spill lists
-        rc = launch_assemble_cst(nx, nxi, g.d_xi, grid_type, (char*)g.scratch + 64, nblocks, counter, g.cst_res,
-                                 g.cst_last, g.cst_ifail, st);
+    const int queue = (mode && mode[0] == 'q') ? 1 : 0;
+    const size_t need = qags_lists_bytes(sms) + 64;                // 7 counters, then the interval-list spill area
+    if (g.scratch_bytes < need) {
+        if (g.scratch) cudaFree(g.scratch);
+        g.scratch = nullptr;
+        g.scratch_bytes = 0;
+        CUDA_OK(cudaMalloc(&g.scratch, need));
+        g.scratch_bytes = need;
     }
+    nvtx_push("tkb K2 QAGS constants");
+    const int rc = launch_assemble_cst(nx, nxi, g.d_xi, grid_type, (char*)g.scratch + 64, sms, queue,
+                                       (unsigned long long*)g.scratch, g.cst_res, g.cst_last, g.cst_ifail, st, g.side,
+                                       g.fork, g.join);
+    nvtx_pop();
     if (overlap_k1) {
         CUDA_OK(cudaEventRecord(g.k1_fork, st));                 // after the K2 launches were issued: ordering hint only
         CUDA_OK(cudaStreamWaitEvent(g.k1_stream, g.ev[0], 0));   // data dependency: the xi upload
         CUDA_OK(cudaEventRecord(g.ev[5], g.k1_stream));
-        if (launch_assemble_fixed(nx, nxi, g.d_xi, grid_type, g.P, g.diag, g.k1_stream)) return 1;
+        nvtx_push("tkb K1 fixed quadrature");
+        const int rc1 = launch_assemble_fixed(nx, nxi, g.d_xi, grid_type, g.P, g.diag, g.k1_stream);
+        nvtx_pop();
+        if (rc1) return 1;
         CUDA_OK(cudaEventRecord(g.k1_done, g.k1_stream));
         CUDA_OK(cudaStreamWaitEvent(st, g.k1_done, 0));
     }
@@ -281,9 +223,11 @@ static int ensure_composed(int nfl, cudaStream_t st)
     const size_t nn = (size_t)g.nx * g.nx * g.nxi;
     for (int k = 0; k < 7; k++)
         if (!c.a[k]) CUDA_OK(cudaMalloc(&c.a[k], sizeof(double) * nn * (k < 3 ? 1 : 4)));
-    if (launch_compose(g.nx, g.nxi, nfl, g.P, g.diag, g.cst_res, c.a[0], c.a[1], c.a[2], c.a[3], c.a[4], c.a[5],
-                       c.a[6], st))
-        return 1;
+    nvtx_push("tkb K3 compose nfl slice");
+    const int rc3 = launch_compose(g.nx, g.nxi, nfl, g.P, g.diag, g.cst_res, c.a[0], c.a[1], c.a[2], c.a[3], c.a[4], c.a[5],
+                                   c.a[6], st);
+    nvtx_pop();
+    if (rc3) return 1;
     c.valid = true;
     return 0;
 }
@@ -348,6 +292,7 @@ static int make_matrices_impl(int nq2, const double* q2_host, int nlo, cudaStrea
     double* ws = g.ws;
     CUDA_OK(cudaEventRecord(g.ev[3], st));
     int rc = 0;
+    nvtx_push("tkb K4 RK4 stepping");
     // composed-array indices: 0 NS0, 1 NS1p, 2 NS1m, 3 SGV0, 4 SGA0, 5 SGV1, 6 SGA1
     rc = rc || step_type(n, g.q2, g.lnlo, 0, 1, g.M[0], ws, st);
     if (!rc) {
@@ -359,6 +304,7 @@ static int make_matrices_impl(int nq2, const double* q2_host, int nlo, cudaStrea
     }
     rc = rc || step_type(2 * n, g.q2, g.lnlo, 3, 5, g.M[2], ws, st);
     rc = rc || step_type(2 * n, g.q2, g.lnlo, 4, 6, g.M[3], ws, st);
+    nvtx_pop();
     cudaEventRecord(g.ev[4], st);
     g.ev_m = true;
     cudaError_t e = cudaStreamSynchronize(st);
@@ -491,7 +437,10 @@ int tkb_apply(int m, int nxi, int nq2, int64_t S, const double* M_dev, const dou
               double* out_dev, void* stream)
 {
     if (m < 1 || nxi < 1 || nq2 < 1 || S < 0 || !M_dev || !g_dev || !out_dev) return set_error("tkb_apply: bad arguments");
-    return launch_apply(m, nxi, nq2, S, M_dev, g_dev, ldg, S, out_dev, (cudaStream_t)stream);
+    nvtx_push("tkb K5 apply");
+    const int rc = launch_apply(m, nxi, nq2, S, M_dev, g_dev, ldg, S, out_dev, (cudaStream_t)stream);
+    nvtx_pop();
+    return rc;
 }
 
 int tkb_apply_strided(int m, int nxi, int nq2, int64_t S, const double* M_dev, const double* g_dev, int64_t ldg,
@@ -499,7 +448,10 @@ int tkb_apply_strided(int m, int nxi, int nq2, int64_t S, const double* M_dev, c
 {
     if (m < 1 || nxi < 1 || nq2 < 1 || S < 0 || !M_dev || !g_dev || !out_dev || xig < 0 || ldg < 0)
         return set_error("tkb_apply_strided: bad arguments");
-    return launch_apply(m, nxi, nq2, S, M_dev, g_dev, ldg, xig, out_dev, (cudaStream_t)stream);
+    nvtx_push("tkb K5 apply");
+    const int rc = launch_apply(m, nxi, nq2, S, M_dev, g_dev, ldg, xig, out_dev, (cudaStream_t)stream);
+    nvtx_pop();
+    return rc;
 }
 
 int64_t tkb_evolve_workspace(int nx, int nxi, int nq2, int64_t S, int nfl)
@@ -517,8 +469,11 @@ int tkb_evolve_fixed_flavor(int nx, int nxi, int nq2, int64_t S, int nfl, int F,
         skip > nq2 || q0 < 0 || ldq < q0 + (nq2 - skip) || !tpls_host || !tpls_inv_host || !M_sg_dev || !M_nsp_dev ||
         !M_nsm_dev || !gpd_dev || !out_dev || !work_dev)
         return set_error("tkb_evolve_fixed_flavor: bad arguments");
-    return launch_evolve_fixed_flavor(nx, nxi, nq2, S, nfl, F, Fout, tpls_host, tpls_inv_host, M_sg_dev, M_nsp_dev, M_nsm_dev,
-                                      gpd_dev, out_dev, ldq, q0, skip, work_dev, (cudaStream_t)stream);
+    nvtx_push("tkb K7 evolve_fixed_flavor");
+    const int rc = launch_evolve_fixed_flavor(nx, nxi, nq2, S, nfl, F, Fout, tpls_host, tpls_inv_host, M_sg_dev, M_nsp_dev,
+                                              M_nsm_dev, gpd_dev, out_dev, ldq, q0, skip, work_dev, (cudaStream_t)stream);
+    nvtx_pop();
+    return rc;
 }
 
 int tkb_gk(int which, int nx, int nxi, int nt, const double* x_dev, const double* xi_dev, const double* t_dev,
@@ -534,9 +489,8 @@ int tkb_free(void)
     free_kernels();
     if (g.scratch) cudaFree(g.scratch);
     if (g.ws) cudaFree(g.ws);
-    if (g.qlog) cudaFree(g.qlog);
-    g.scratch = nullptr; g.ws = nullptr; g.qlog = nullptr;
-    g.scratch_bytes = g.ws_bytes = g.qlog_bytes = 0;
+    g.scratch = nullptr; g.ws = nullptr;
+    g.scratch_bytes = g.ws_bytes = 0;
     return 0;
 }
 

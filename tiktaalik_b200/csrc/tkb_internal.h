@@ -10,30 +10,19 @@ namespace tkb {
 enum DiagSlot : int { DIAG_FX = 0, DIAG_X, DIAG_K0QQ, DIAG_A0GG, DIAG_A0GGN, DIAG_N = 8 };
 
 int set_error(const char* msg);          // stores the message, returns 1
+void nvtx_push(const char* name);        // NVTX ranges around the stages K1 .. K5 (libnvToolsExt bound at run time; no-ops without it)
+void nvtx_pop();
 extern long long g_launches;             // kernel launches issued by the library
 
 // assemble.cu
-size_t qags_scratch_bytes();
-int assemble_cst_warps_per_block();
 int set_grid_variant(int eta_recip_f32, int x0_recip_f32);
 size_t pre_table_doubles(size_t rows);
 int launch_pre_table(int n, int nxi, const double* xi_dev, int grid_type, double* tab, cudaStream_t st);
 int launch_assemble_fixed(int n, int nxi, const double* xi_dev, int grid_type, double* P, double* diag, cudaStream_t st);
-int launch_assemble_cst(int n, int nxi, const double* xi_dev, int grid_type, void* scratch, int nblocks,
-                        unsigned long long* counter, double* cst_res, int* cst_last, int* cst_ifail, cudaStream_t st);
-int launch_assemble_cst_batched(int n, int nxi, const double* xi_dev, int grid_type, void* lists, int nblocks,
-                                unsigned long long* counters, double* cst_res, int* cst_last, int* cst_ifail,
-                                cudaStream_t st, cudaStream_t* side, cudaEvent_t fork, cudaEvent_t* join);
-size_t qags_replay_lists_bytes(int nblocks);
-size_t qags_replay_log_doubles(int which, size_t ninst, int L);
-int launch_assemble_cst_replay(int n, int nxi, const double* xi_dev, int grid_type, void* lists, int sms,
-                               unsigned long long* counters, double* cst_res, int* cst_last, int* cst_ifail,
-                               double* log_ns, double* log_gg, int* nlog_ns, int* nlog_gg, int L,
-                               cudaStream_t st, cudaStream_t* side, cudaEvent_t fork, cudaEvent_t* join,
-                               cudaEvent_t* leader_done);
-size_t qags_batched_bytes_per_block();
-int qags_batched_instances_per_block();
-int qags_batched_blocks_per_sm();
+size_t qags_lists_bytes(int sms);
+int launch_assemble_cst(int n, int nxi, const double* xi_dev, int grid_type, void* lists, int sms, int queue,
+                        unsigned long long* counters, double* cst_res, int* cst_last, int* cst_ifail,
+                        cudaStream_t st, cudaStream_t* side, cudaEvent_t fork, cudaEvent_t* join);
 int launch_compose(int n, int nxi, int nfl, const double* P, const double* diag, const double* cst_res,
                    double* NS0, double* NS1p, double* NS1m, double* SGV0, double* SGA0, double* SGV1, double* SGA1,
                    cudaStream_t st);
