@@ -131,6 +131,11 @@ int tkb_set_variant(int eta_recip_f32, int x0_recip_f32);
 int tkb_shard_unique_id(char id_out[128]);
 int tkb_shard_init(const char id_in[128], int rank, int world);
 int tkb_allgather_matrices(int type, int nstype, const int* nxi_per_rank, double* dev_out, void* stream);
+/* the same for a xi list sharded by STRIDE (rank r holds xi[r], xi[r + world], ...; every rank the same number of
+ * them): this rank's current matrices, local xi k = 0 .. nxi - 1, go to dev_out[(k_first + k) * world + rank][nq2][m][m],
+ * so the gathered array is in the order of the global list.  k_first > 0 gathers a later chunk of the rank's xi
+ * (a sweep processed in chunks, each chunk's gather running under the next chunk's assembly on another stream). */
+int tkb_allgather_matrices_strided(int type, int nstype, int k_first, double* dev_out, void* stream);
 int tkb_shard_finalize(void);
 
 /* releases every device buffer of the implicit context */

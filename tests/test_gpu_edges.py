@@ -159,6 +159,22 @@ def test_apply_empty_and_strided_inputs(tk):
     assert torch.allclose(out[fin], ref[fin], rtol=1e-12, atol=1e-12 * float(ref[fin].abs().max()))
 
 
+def test_apply_more_than_65535_matrices_with_shared_right_hand_side(tk):
+    """nxi * nQ2 > 65535 with nQ2 = 16 (e.g. the gathered C5 non-singlet set, 4096 xi x 16 Q2): the batch goes to the
+    GEMM in gridDim.z chunks, which must start at a multiple of nQ2 because the nQ2 matrices of a xi share one
+    right-hand side."""
+    m, nxi, nq, S = 40, 4097, 16, 3
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    M = torch.rand((nxi, nq, m, m), generator=gen, dtype=torch.float64, device="cuda") - 0.5
+    g = torch.rand((m, nxi, S), generator=gen, dtype=torch.float64, device="cuda")
+    out = torch.empty((nxi, nq, m, S), dtype=torch.float64, device="cuda")
+    L = tk._lib.lib()
+    tk._lib.check(L.tkb_apply(m, nxi, nq, S, tk._lib.ptr(M), tk._lib.ptr(g), nxi * S, tk._lib.ptr(out), tk._lib.stream_ptr()))
+    torch.cuda.synchronize()
+    ref = torch.einsum("kqij,jks->kqis", M, g)
+    assert float((out - ref).abs().max()) < 1e-12 * float(ref.abs().max())
+
+
 def test_many_xi_few_rows_queue_drains(tk, tko):
     """More QAGS instances than slots and fewer than one full round of them at the end: the persistent
     blocks must drain the queue and terminate (both groups of the pipeline, all constants)."""

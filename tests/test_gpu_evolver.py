@@ -51,7 +51,7 @@ def _evolve_fixed(g, M_SG, M_NSp, M_NSm, nfl):
 def _oracle_evolve_gpds(tko, nx, xi, grid_type, Q2, gpd, gpd_type, nlo, mc2, mb2, eps=1e-6):
     """Evolver.evolveGPDs (evolution.py:121-213) with oracle matrices"""
     tko.initialize_kernels(nx, xi, grid_type, mode=1)
-    new = _pad(gpd[..., None], 5 - (gpd.shape[0] - 1))
+    new = _pad(gpd[..., None], max(0, 5 - (gpd.shape[0] - 1)))
     pass_c = Q2[0] < mc2 - eps and Q2[-1] > mc2 + eps
     pass_b = Q2[0] < mb2 - eps and Q2[-1] > mb2 + eps
     segs = []
@@ -89,6 +89,21 @@ def test_evolver_evolve_gpds_through_thresholds(tk, tko, gpd_type, nlo):
     _close(got.cpu().numpy(), ref)
     # the first Q2 slice is the (padded) input; heavy flavours start at zero
     assert np.array_equal(got[:4, ..., 0].cpu().numpy(), gpd) and float(got[4:, ..., 0].abs().max()) == 0.0
+
+
+def test_evolver_accepts_a_seven_row_grid(tk, tko):
+    """gluon + six quark rows (g, u, d, s, c, b, t): the reference keeps the extra row and zero-pads it after the
+    first Q2 point through add_pad (evolution.py:150-153, 495-514); ADVICE round 1: the library refused Fout > 6"""
+    nx, xi = 16, np.array([0.3, 0.6])
+    ev = tk.Evolver(nx=nx, xi=xi, nQ2=5, Q2i=1.2, Q2f=30.0, grid_type=1)
+    x = tko.pixelspace(nx)
+    base = np.stack([tko.gk(n, x, xi, [0.0]) for n in ("Hg", "Hu", "Hd", "Hs")], axis=0)[..., 0]       # (4, nx, nxi)
+    rng = np.random.default_rng(5)
+    gpd = np.concatenate((base, 0.1 * rng.standard_normal((3, nx, 2))), axis=0)                       # 7 rows
+    got = ev.evolveGPDs(gpd, gpd_type='V', nlo=True)
+    assert tuple(got.shape) == (7, nx, 2, 5)
+    ref = _oracle_evolve_gpds(tko, nx, xi, 1, ev.Q2, gpd, 'V', True, tk.pars.mc2, tk.pars.mb2)
+    _close(got.cpu().numpy(), ref)
 
 
 def test_evolver_single_sector_methods(tk, tko):

@@ -87,13 +87,17 @@ def test_basis_helpers_on_cpu_tensors():
 
 def test_xi_partition_and_clamp():
     from tiktaalik_b200 import shard
-    counts, offs = shard.xi_partition(10, 4)
+    counts, offs = shard.xi_partition(10, 4, "blocks")
     assert counts == [3, 3, 2, 2] and offs == [0, 3, 6, 8]
+    counts, offs = shard.xi_partition(10, 4)                                   # strided (default): rank r holds r, r + 4, ...
+    assert counts == [3, 3, 2, 2] and offs == [0, 1, 2, 3]
     xi = np.array([1e-7, 0.1, 0.5, 0.9999999])
     c = shard.clamp_xi(xi)
     assert c[0] == 1e-6 and c[-1] == 0.999999 and xi[0] == 1e-7               # matevo.f90:688-689, input untouched
-    parts = [shard.local_xi(xi, r, 2)[0] for r in range(2)]
+    parts = [shard.local_xi(xi, r, 2, "blocks")[0] for r in range(2)]
     assert np.array_equal(np.concatenate(parts), c)
+    parts = [shard.local_xi(xi, r, 2)[0] for r in range(2)]
+    assert np.array_equal(parts[0], c[0::2]) and np.array_equal(parts[1], c[1::2])
 
 
 def test_gk_model_matches_oracle(tko):

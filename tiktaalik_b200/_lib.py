@@ -52,6 +52,7 @@ SIGNATURES = {
     "tkb_shard_unique_id": (C.c_int, [C.c_char_p]),
     "tkb_shard_init": (C.c_int, [C.c_char_p, C.c_int, C.c_int]),
     "tkb_allgather_matrices": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int), C.c_void_p, C.c_void_p]),
+    "tkb_allgather_matrices_strided": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "tkb_shard_finalize": (C.c_int, []),
     "tkb_fp64_peak": (C.c_int, [_dp]),
 }

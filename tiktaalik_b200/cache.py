@@ -28,7 +28,12 @@ def _store_order(M):
 def save_matrices(path, mats, nx, xi, Q2, nlo, grid_type=1):
     """mats: dict type -> tensor of logical shape (m, m, nxi, nQ2) as returned by the matrices getters"""
     os.makedirs(path, exist_ok=True)
-    xi = np.atleast_1d(np.asarray(xi, dtype=np.float64))
+    # the matrices were built for the clamped list (matevo.f90:688-689: first >= 1e-6, last <= 0.999999)
+    xi = np.array(np.atleast_1d(xi), dtype=np.float64)
+    if xi.shape[0] and xi[0] < 1e-6:
+        xi[0] = 1e-6
+    if xi.shape[0] and xi[-1] > 0.999999:
+        xi[-1] = 0.999999
     Q2 = np.asarray(Q2, dtype=np.float64)
     for name, M in mats.items():
         if name not in TYPES:

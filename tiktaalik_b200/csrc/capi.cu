@@ -47,6 +47,7 @@ struct Composed {              // one nfl slice (matevo.f90:35-39), row-major pe
 };
 
 struct Context {
+    int device = -1;            // the CUDA device the context (streams, events, buffers) is bound to
     int nx = 0, nxi = 0, grid_type = 1, nq2 = 0, lnlo = 0;
     std::vector<double> xi, q2;
     double* d_xi = nullptr;
@@ -109,6 +110,12 @@ static void free_kernels()
 
 static int ensure_events()
 {
+    int dev = 0;
+    CUDA_OK(cudaGetDevice(&dev));
+    if (g.device >= 0 && g.device != dev)
+        return set_error("the library's context is bound to another CUDA device: call tkb_free() on that device first "
+                         "(one implicit context per process, like the reference's module state)");
+    g.device = dev;
     for (auto& e : g.ev)
         if (!e) CUDA_OK(cudaEventCreate(&e));
     if (!g.fork) {
@@ -278,9 +285,10 @@ static int make_matrices_impl(int nq2, const double* q2_host, int nlo, cudaStrea
         for (int t = 0; t < 4; t++) CUDA_OK(cudaMalloc(&g.M[t], sizeof(double) * nn * (t < 2 ? 1 : 4)));
         g.M_elems = nn;
     }
-    g.q2.assign(q2_host, q2_host + nq2);
-    g.nq2 = nq2;
-    g.lnlo = nlo ? 1 : 0;
+    // the schedule becomes visible to the getters only after the stepping has succeeded
+    invalidate_matrices();
+    const std::vector<double> q2v(q2_host, q2_host + nq2);
+    const int lnlo = nlo ? 1 : 0;
     const size_t ws_need = sizeof(double) * (size_t)4 * n * n * nxi * 7;
     if (g.ws_bytes < ws_need) {
         if (g.ws) cudaFree(g.ws);
@@ -294,16 +302,16 @@ static int make_matrices_impl(int nq2, const double* q2_host, int nlo, cudaStrea
     int rc = 0;
     nvtx_push("tkb K4 RK4 stepping");
     // composed-array indices: 0 NS0, 1 NS1p, 2 NS1m, 3 SGV0, 4 SGA0, 5 SGV1, 6 SGA1
-    rc = rc || step_type(n, g.q2, g.lnlo, 0, 1, g.M[0], ws, st);
+    rc = rc || step_type(n, q2v, lnlo, 0, 1, g.M[0], ws, st);
     if (!rc) {
-        if (g.lnlo) rc = step_type(n, g.q2, g.lnlo, 0, 2, g.M[1], ws, st);
+        if (lnlo) rc = step_type(n, q2v, lnlo, 0, 2, g.M[1], ws, st);
         else {   // at LO the minus-type matrix is the plus-type one (matevo.f90:517-520 with l_nlo false)
             cudaError_t e = cudaMemcpyAsync(g.M[1], g.M[0], sizeof(double) * nn, cudaMemcpyDeviceToDevice, st);
             if (e != cudaSuccess) rc = set_error(cudaGetErrorString(e));
         }
     }
-    rc = rc || step_type(2 * n, g.q2, g.lnlo, 3, 5, g.M[2], ws, st);
-    rc = rc || step_type(2 * n, g.q2, g.lnlo, 4, 6, g.M[3], ws, st);
+    rc = rc || step_type(2 * n, q2v, lnlo, 3, 5, g.M[2], ws, st);
+    rc = rc || step_type(2 * n, q2v, lnlo, 4, 6, g.M[3], ws, st);
     nvtx_pop();
     cudaEventRecord(g.ev[4], st);
     g.ev_m = true;
@@ -314,6 +322,9 @@ static int make_matrices_impl(int nq2, const double* q2_host, int nlo, cudaStrea
         snprintf(buf, sizeof buf, "evolution-matrix stepping failed: %s", cudaGetErrorString(e));
         return set_error(buf);
     }
+    g.q2 = q2v;
+    g.nq2 = nq2;
+    g.lnlo = lnlo;
     return 0;
 }
 
@@ -465,7 +476,7 @@ int tkb_evolve_fixed_flavor(int nx, int nxi, int nq2, int64_t S, int nfl, int F,
                             const double* M_nsm_dev, const double* gpd_dev, double* out_dev, int64_t ldq, int q0, int skip,
                             double* work_dev, void* stream)
 {
-    if (nx < 1 || nxi < 1 || nq2 < 1 || S < 0 || nfl < 1 || nfl > 5 || F < 1 || Fout < nfl + 1 || Fout > 6 || skip < 0 ||
+    if (nx < 1 || nxi < 1 || nq2 < 1 || S < 0 || nfl < 1 || nfl > 5 || F < 1 || Fout < nfl + 1 || skip < 0 ||
         skip > nq2 || q0 < 0 || ldq < q0 + (nq2 - skip) || !tpls_host || !tpls_inv_host || !M_sg_dev || !M_nsp_dev ||
         !M_nsm_dev || !gpd_dev || !out_dev || !work_dev)
         return set_error("tkb_evolve_fixed_flavor: bad arguments");
@@ -491,6 +502,20 @@ int tkb_free(void)
     if (g.ws) cudaFree(g.ws);
     g.scratch = nullptr; g.ws = nullptr;
     g.scratch_bytes = g.ws_bytes = 0;
+    // streams and events belong to the device the context was bound to; after tkb_free another device may bind
+    for (auto& e : g.ev) { if (e) cudaEventDestroy(e); e = nullptr; }
+    for (int k = 0; k < 7; k++) {
+        if (g.side[k]) cudaStreamDestroy(g.side[k]);
+        if (g.join[k]) cudaEventDestroy(g.join[k]);
+        g.side[k] = nullptr; g.join[k] = nullptr;
+    }
+    if (g.k1_stream) cudaStreamDestroy(g.k1_stream);
+    if (g.k1_fork) cudaEventDestroy(g.k1_fork);
+    if (g.k1_done) cudaEventDestroy(g.k1_done);
+    if (g.fork) cudaEventDestroy(g.fork);
+    g.k1_stream = nullptr; g.k1_fork = g.k1_done = g.fork = nullptr;
+    g.ev_k = g.ev_m = false;
+    g.device = -1;
     return 0;
 }
 

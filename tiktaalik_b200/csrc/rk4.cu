@@ -393,10 +393,12 @@ int launch_gemm(int M, int N, int K, double alpha,
     if (bdivB < 1) bdivB = 1;
     // 80-wide tiles divide nx = 80/160/320 exactly; otherwise 64-wide; narrow N uses 32-wide
     const bool t5 = (M % 80 == 0) && (N % 80 == 0);
-    const int maxz = 65535;
+    // gridDim.z <= 65535: larger batches go in chunks whose starts are multiples of bdivB, so that the right-hand
+    // side shared by bdivB consecutive A's (the nQ2 matrices of one xi in the application) stays with its group
+    if (bdivB > 65535) return set_error("launch_gemm: more than 65535 matrices share one right-hand side");
+    const int maxz = (65535 / bdivB) * bdivB;
     for (int b0 = 0; b0 < batch; b0 += maxz) {
         const int nb = (batch - b0 < maxz) ? (batch - b0) : maxz;
-        if ((b0 % bdivB) != 0) return set_error("launch_gemm: batch chunk not aligned with bdivB");
         const double* Ab = A + (int64_t)b0 * strideA;
         const double* Bb = B + (int64_t)(b0 / bdivB) * strideB;
         const double* Db = D ? D + (int64_t)b0 * strideD : nullptr;

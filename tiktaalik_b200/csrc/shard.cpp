@@ -6,6 +6,10 @@
 // array is the concatenation of the slabs in rank order.  Equal blocks go through ncclAllGather; when the block
 // sizes differ between ranks the gather is one NCCL group of `world` broadcasts (root r writes slab r).
 //
+// A xi list sharded by STRIDE (rank r holds xi[r], xi[r + world], ...: every rank sees the same mix of the xi-dependent
+// QAGS cost, which varies by 1.5x along the benchmark's list) is gathered straight into the order of the global list
+// by one NCCL group of per-xi all-gathers: the all-gather of local xi k lands in out[k * world + 0 .. world - 1].
+//
 // NCCL is bound at run time (dlopen of libnccl.so.2 -- inside a PyTorch process that is the copy torch has
 // already loaded) so that the library has no link-time dependency on it and single-GPU use never touches it.
 #include <cuda_runtime.h>
@@ -132,6 +136,28 @@ int tkb_allgather_matrices(int type, int nstype, const int* nxi_per_rank, double
             if (rc != 0) { N.GroupEnd(); return nccl_fail("ncclBroadcast", rc); }
         }
         off += count;
+    }
+    rc = N.GroupEnd();
+    if (rc != 0) return nccl_fail("ncclGroupEnd", rc);
+    return 0;
+}
+
+int tkb_allgather_matrices_strided(int type, int nstype, int k_first, double* dev_out, void* stream)
+{
+    if (!N.comm) return tkb::set_error("tkb_allgather_matrices_strided: call tkb_shard_init first");
+    if (!dev_out || k_first < 0) return tkb::set_error("tkb_allgather_matrices_strided: bad arguments");
+    const double* local = nullptr;
+    int64_t shape[4], strides[4];
+    if (tkb_evomatrix(type, nstype, &local, shape, strides)) return 1;
+    const int64_t m = shape[0], nxi = shape[2], nq2 = shape[3];
+    const size_t per_xi = (size_t)nq2 * (size_t)m * (size_t)m;
+    int rc = N.GroupStart();
+    if (rc != 0) return nccl_fail("ncclGroupStart", rc);
+    for (int64_t k = 0; k < nxi; k++) {
+        // local xi k of every rank -> global positions (k_first + k) * world + rank: the global list's order
+        rc = N.AllGather(local + (size_t)k * per_xi, dev_out + (size_t)(k_first + k) * (size_t)N.world * per_xi, per_xi,
+                         kNcclFloat64, N.comm, (cudaStream_t)stream);
+        if (rc != 0) { N.GroupEnd(); return nccl_fail("ncclAllGather", rc); }
     }
     rc = N.GroupEnd();
     if (rc != 0) return nccl_fail("ncclGroupEnd", rc);

@@ -247,13 +247,21 @@ class Evolver:
         return
 
     def _make_segment(self, seg, Q2):
-        # LO first, then NLO (reference: evolution.py:381-429)
-        for order, nlo in (("LO", False), ("NLO", True)):
-            matrices.initialize_evolution_matrices(Q2, nlo=nlo)
-            setattr(self, "Mevo_VNS_%s_%s" % (order, seg), matrices.matrix_VNS())
-            setattr(self, "Mevo_ANS_%s_%s" % (order, seg), matrices.matrix_ANS())
-            setattr(self, "Mevo_VSG_%s_%s" % (order, seg), matrices.matrix_VSG())
-            setattr(self, "Mevo_ASG_%s_%s" % (order, seg), matrices.matrix_ASG())
+        # LO first, then NLO (reference: evolution.py:381-429).  The cached matrices outlive the next
+        # initialize_evolution_matrices call, which rewrites the library's storage in place, so they are always
+        # private copies -- also when the getters are switched to zero-copy views (f90wrap.matrices.dummy.zero_copy).
+        f90 = matrices.f90src
+        keep = getattr(f90, "zero_copy", False)
+        f90.zero_copy = False
+        try:
+            for order, nlo in (("LO", False), ("NLO", True)):
+                matrices.initialize_evolution_matrices(Q2, nlo=nlo)
+                setattr(self, "Mevo_VNS_%s_%s" % (order, seg), matrices.matrix_VNS())
+                setattr(self, "Mevo_ANS_%s_%s" % (order, seg), matrices.matrix_ANS())
+                setattr(self, "Mevo_VSG_%s_%s" % (order, seg), matrices.matrix_VSG())
+                setattr(self, "Mevo_ASG_%s_%s" % (order, seg), matrices.matrix_ASG())
+        finally:
+            f90.zero_copy = keep
 
     def makeEvolutionMatrices_mc2(self,Q2):
         ''' Matrices up to mc2, if the charm threshold is passed. '''

@@ -90,7 +90,14 @@ def get_nfl(Q2):
 # Routines to create evolution matrices
 
 def _scrub(M):
-    # reference: M[np.isnan(M)] = 0; M[np.isinf(M)] = 0 (matrices.py:146-147); in place like there
+    # reference: M[np.isnan(M)] = 0; M[np.isinf(M)] = 0 (matrices.py:146-147).  The getters' default result is a
+    # private copy and is scrubbed in place like there; a zero-copy view (f90src.zero_copy) is a window on the
+    # library's own storage, which must not be rewritten: it is returned as it is when every entry is finite
+    # and copied otherwise.
+    if getattr(f90src, "zero_copy", False):
+        if bool(torch.isfinite(M).all()):
+            return M
+        return torch.nan_to_num(M, nan=0.0, posinf=0.0, neginf=0.0)
     return torch.nan_to_num_(M, nan=0.0, posinf=0.0, neginf=0.0)
 
 def matrix_VNS(ns_type=1):

@@ -29,15 +29,36 @@ for n, ref in full.items():
     got = tk.shard.gather_matrix(getattr(tk.matrices, n)())
     same = tuple(got.shape) == tuple(ref.shape) and torch.equal(got, ref)
     ok = ok and same
-# the same gather through the C ABI (tkb_shard_init / tkb_allgather_matrices)
-counts, _ = tk.shard.xi_partition(xi.shape[0], world)
+# the same gather through the C ABI (tkb_shard_init / tkb_allgather_matrices[_strided]), both layouts; the strided
+# layout also on a list with equal shares (the per-xi NCCL group) gathered in two chunks of local xi
 tk.shard.init_capi()
-for n, ref in full.items():
-    got = tk.shard.gather_matrix_capi(n, counts)
-    torch.cuda.synchronize()
-    same = tuple(got.shape) == tuple(ref.shape) and torch.equal(got, ref)
+for layout in ("strided", "blocks"):
+    counts, _ = tk.shard.xi_partition(xi.shape[0], world, layout)
+    tk.shard.initialize_kernels_sharded(nx, xi, grid_type=gt, rank=rank, world_size=world, layout=layout)
+    tk.matrices.initialize_evolution_matrices(Q2, nlo=True)
+    for n, ref in full.items():
+        got = tk.shard.gather_matrix_capi(n, counts, layout=layout)
+        torch.cuda.synchronize()
+        same = tuple(got.shape) == tuple(ref.shape) and torch.equal(got, ref)
+        if not same:
+            print("rank %d: C-ABI gather (%s) of %s differs" % (rank, layout, n))
+        ok = ok and same
+xi_even = tk.shard.clamp_xi(xi[:2 * world])
+tk.matrices.initialize_kernels(nx, xi_even, grid_type=gt)
+tk.matrices.initialize_evolution_matrices(Q2, nlo=True)
+full_even = {n: getattr(tk.matrices, n)().clone() for n in full}
+outs = {n: torch.empty((2 * world, Q2.shape[0], r.shape[0], r.shape[0]), dtype=torch.float64, device="cuda") for n, r in full_even.items()}
+for chunk in range(2):                 # one local xi per chunk: k_first = chunk
+    mine_c = xi_even[rank::world][chunk:chunk + 1]
+    tk.shard.f90src.make_kernels_shard(nx, mine_c, gt, 0, 0)
+    tk.matrices.initialize_evolution_matrices(Q2, nlo=True)
+    for n in full_even:
+        tk.shard.gather_matrix_capi(n, [2] * world, out=outs[n], layout="strided", k_first=chunk)
+torch.cuda.synchronize()
+for n, ref in full_even.items():
+    same = torch.equal(outs[n].permute(2, 3, 0, 1), ref)
     if not same:
-        print("rank %d: C-ABI gather of %s differs" % (rank, n))
+        print("rank %d: chunked strided gather of %s differs" % (rank, n))
     ok = ok and same
 # bandwidth of the one exchange step at the bench's size (nx = 160, 256 xi per rank, Q2 4 -> 10): each rank
 # receives (world - 1) slabs of every matrix family over NVLink; device-timed, max over ranks
