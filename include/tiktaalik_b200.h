@@ -138,6 +138,20 @@ int tkb_allgather_matrices(int type, int nstype, const int* nxi_per_rank, double
 int tkb_allgather_matrices_strided(int type, int nstype, int k_first, double* dev_out, void* stream);
 int tkb_shard_finalize(void);
 
+/* the exchange by the copy engines instead (no NCCL, no SMs: it runs UNDER the QAGS kernels, which own every SM for the
+ * whole assembly): every rank pushes its per-xi slabs into the receive buffers of all ranks with one strided
+ * device-to-device copy per peer over NVLink.  tkb_p2p_alloc: this rank's receive buffer of `slot` (0..3, one per
+ * matrix family), a cudaMalloc allocation of `bytes` = nxi_total * nq2 * m * m * 8; tkb_p2p_handle: its 64-byte CUDA IPC
+ * handle, which the host program hands to every rank (world * 64 bytes, rank order); tkb_p2p_open: maps the peers'
+ * buffers; tkb_p2p_push_matrices: this rank's current matrices, local xi k -> [(k_first + k) * world + rank] of every
+ * rank's buffer (the order of the global xi list for a strided split), enqueued on `stream`; the data is complete on a
+ * rank when every rank's push has finished (synchronise the ranks before reading); tkb_p2p_close unmaps and frees. */
+int tkb_p2p_alloc(int slot, int64_t bytes, double** dev_ptr);
+int tkb_p2p_handle(int slot, char handle_out[64]);
+int tkb_p2p_open(int slot, int rank, int world, const char* handles_all);
+int tkb_p2p_push_matrices(int slot, int type, int nstype, int k_first, void* stream);
+int tkb_p2p_close(void);
+
 /* releases every device buffer of the implicit context */
 int tkb_free(void);
 
@@ -151,6 +165,11 @@ int tkb_raw_kernel(int which, int nfl, const double** dev_ptr, void* stream);
 /* all 22 two-variable kernels at npts points: out[p][22] */
 int tkb_eval_kernels(int npts, const double* x_dev, const double* y_dev, const double* xi_dev, double* out_dev,
                      void* stream);
+/* the QAGS integrand K(x,y,xi) - K(y,x,xi) of constant c (index as in tkb_qags_info; kernels_nlo.f90:71-77 and its
+ * siblings) at npts points, evaluated straight from the reference formulas (all four half kernels, nothing skipped):
+ * the unit of ALGORITHMIC work of the QAGS kernels' roofline, and a parity hook */
+int tkb_eval_integrand(int c, int npts, const double* x_dev, const double* y_dev, const double* xi_dev, double* out_dev,
+                       void* stream);
 /* the task skipping of the assembly kernels, exposed for the tests: for constant c (index as in tkb_qags_info) and
  * the four half-kernel tasks of a node (K(x,y) halves 0/1, K(y,x) halves 0/1): support class (2 full, 1 erbl-only,
  * 0 skipped as an exact zero), value of the full evaluation, value of the erbl-only evaluation; arrays [npts][4].

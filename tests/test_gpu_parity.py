@@ -118,6 +118,29 @@ def test_all_kernel_functions_bit_identical(tk, tko, xi):
     assert ok.all(), "kernels not bit-identical: %s" % sorted(set(np.nonzero(~ok)[1].tolist()))
 
 
+@pytest.mark.parametrize("xi", [0.3, 2e-3])
+def test_qags_integrand_hook_bit_identical(tk, tko, xi):
+    """tkb_eval_integrand: K(x,y,xi) - K(y,x,xi) of the seven plus-prescription constants (kernels_nlo.f90:71-77),
+    the straight evaluation whose FP64 instruction count calibrates the K2 roofline"""
+    rng = np.random.default_rng(9)
+    n = 600
+    x = rng.uniform(-1, 1, n)
+    y = rng.uniform(-1, 1, n)
+    x[: n // 3] *= xi * 1.5
+    y[n // 6: n // 2] *= xi * 1.5
+    L = tk._lib.lib()
+    xd, yd, xid = dev(x), dev(y), dev(np.full(n, xi))
+    for c, f in enumerate((7, 8, 9, 18, 19, 20, 21)):
+        out = torch.empty(n, dtype=torch.float64, device="cuda")
+        tk._lib.check(L.tkb_eval_integrand(c, n, tk._lib.ptr(xd), tk._lib.ptr(yd), tk._lib.ptr(xid), tk._lib.ptr(out),
+                                           tk._lib.stream_ptr()))
+        torch.cuda.synchronize()
+        got = out.cpu().numpy()
+        ref = np.array([tko.kernel(f, x[p], y[p], xi) - tko.kernel(f, y[p], x[p], xi) for p in range(n)])
+        ok = (bits(got) == bits(ref)) | (np.isnan(got) & np.isnan(ref)) | ((got == 0) & (ref == 0))
+        assert ok.all(), (c, int((~ok).sum()))
+
+
 def test_kernel_functions_at_singular_points(tk, tko):
     """x = y, y = +-xi, x = +-xi, zeros and end points: the reference evaluates pieces outside their support and
     multiplies by a vanishing step, so 0 * Inf = NaN, divisions by zero and log(0) must come out the same

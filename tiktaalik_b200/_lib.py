@@ -40,6 +40,7 @@ SIGNATURES = {
     "tkb_qags_info": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "tkb_raw_kernel": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_void_p]),
     "tkb_eval_kernels": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "tkb_eval_integrand": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "tkb_eval_scalar": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "tkb_stage_ms": (C.c_int, [_dp]),
     "tkb_launch_count": (C.c_longlong, []),
@@ -54,6 +55,11 @@ SIGNATURES = {
     "tkb_allgather_matrices": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int), C.c_void_p, C.c_void_p]),
     "tkb_allgather_matrices_strided": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "tkb_shard_finalize": (C.c_int, []),
+    "tkb_p2p_alloc": (C.c_int, [C.c_int, C.c_int64, C.POINTER(C.c_void_p)]),
+    "tkb_p2p_handle": (C.c_int, [C.c_int, C.c_char_p]),
+    "tkb_p2p_open": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_char_p]),
+    "tkb_p2p_push_matrices": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "tkb_p2p_close": (C.c_int, []),
     "tkb_fp64_peak": (C.c_int, [_dp]),
 }
 

@@ -728,6 +728,51 @@ __global__ void eval_scalar_kernel(int which, int npts, const double* __restrict
     }
 }
 
+// calibration / test hook: the QAGS integrand K(x,y,xi) - K(y,x,xi) of constant KID (kernels_nlo.f90:71-77 and its
+// siblings) evaluated straight from the reference formulas -- all four half kernels in full, no support-class
+// skipping, no per-row tables.  Its FP64 instruction count per point is the ALGORITHMIC work of one integrand
+// evaluation that the roofline of K2 is quoted in (profiles/k2_flops_per_eval.json); the tests compare its values
+// with the oracle's kernel functions.
+template <int KID>
+__global__ void eval_integrand_kernel(int npts, const double* __restrict__ xs, const double* __restrict__ ys,
+                                      const double* __restrict__ xis, double* __restrict__ out)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npts) return;
+    const double x = xs[p], y = ys[p], xi = xis[p];
+    const double xx1 = 0.5 * (1.0 + x / xi), xx2 = 0.5 * (1.0 - x / xi);
+    const double yy1 = 0.5 * (1.0 + y / xi), yy2 = 0.5 * (1.0 - y / xi);
+    double h[4];
+#pragma unroll 1
+    for (int k = 0; k < 4; k++) {
+        const int dir = k >> 1, half = k & 1;
+        const double U1 = dir ? yy1 : xx1, U2 = dir ? yy2 : xx2, V1 = dir ? xx1 : yy1, V2 = dir ? xx2 : yy2;
+        double o[NKERN];
+        eval_half<bit(KID), true>(half ? U2 : U1, half ? V2 : V1, half ? U1 : U2, half ? V1 : V2, o);
+        h[k] = o[KID];
+    }
+    out[p] = combine_halves<KID>(h[0], h[1], xi) - combine_halves<KID>(h[2], h[3], xi);
+}
+
+int launch_eval_integrand(int c, int npts, const double* xs, const double* ys, const double* xis, double* out, cudaStream_t st)
+{
+    const int g = (npts + 127) / 128;
+    switch (c) {
+    case 0: eval_integrand_kernel<K_NSP><<<g, 128, 0, st>>>(npts, xs, ys, xis, out); break;
+    case 1: eval_integrand_kernel<K_NSM><<<g, 128, 0, st>>>(npts, xs, ys, xis, out); break;
+    case 2: eval_integrand_kernel<K_NSN><<<g, 128, 0, st>>>(npts, xs, ys, xis, out); break;
+    case 3: eval_integrand_kernel<K_V1GG><<<g, 128, 0, st>>>(npts, xs, ys, xis, out); break;
+    case 4: eval_integrand_kernel<K_A1GG><<<g, 128, 0, st>>>(npts, xs, ys, xis, out); break;
+    case 5: eval_integrand_kernel<K_V1GGN><<<g, 128, 0, st>>>(npts, xs, ys, xis, out); break;
+    case 6: eval_integrand_kernel<K_A1GGN><<<g, 128, 0, st>>>(npts, xs, ys, xis, out); break;
+    default: return set_error("tkb_eval_integrand: constant index out of range");
+    }
+    ++g_launches;
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
+    return 0;
+}
+
 // test hook for the task skipping of K1 / K2: per point and for the four half-kernel tasks of a node
 // (K(x,y) halves 0/1, K(y,x) halves 0/1): the support class the assembly kernels would assign, the value of the
 // full evaluation and the value of the erbl-only evaluation of one QAGS kernel.  The tests require: class 0 =>

@@ -541,6 +541,13 @@ int tkb_eval_kernels(int npts, const double* x_dev, const double* y_dev, const d
 {
     return launch_eval_kernels(npts, x_dev, y_dev, xi_dev, out_dev, (cudaStream_t)stream);
 }
+int tkb_eval_integrand(int c, int npts, const double* x_dev, const double* y_dev, const double* xi_dev, double* out_dev,
+                       void* stream)
+{
+    if (npts < 0 || !x_dev || !y_dev || !xi_dev || !out_dev) return set_error("tkb_eval_integrand: bad arguments");
+    if (npts == 0) return 0;
+    return launch_eval_integrand(c, npts, x_dev, y_dev, xi_dev, out_dev, (cudaStream_t)stream);
+}
 int tkb_eval_scalar(int which, int npts, const double* a_dev, const double* b_dev, double* out_dev, void* stream)
 {
     return launch_eval_scalar(which, npts, a_dev, b_dev, out_dev, (cudaStream_t)stream);

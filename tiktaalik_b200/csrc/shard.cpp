@@ -164,4 +164,109 @@ int tkb_allgather_matrices_strided(int type, int nstype, int k_first, double* de
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// The same exchange without NCCL and without SMs: every rank PUSHES its per-xi slabs into the receive buffers of all
+// ranks with strided device-to-device copies (cudaMemcpy2DAsync: one call per peer and matrix family, row = one xi
+// slab, destination pitch = world slabs), which the copy engines carry over NVLink / NVSwitch.  The QAGS kernels keep
+// every SM's register file and shared memory for the whole assembly, so an NCCL kernel launched next to them only
+// gets to run when they drain; a copy-engine transfer runs under them.  The receive buffers are cudaMalloc
+// allocations of the library, exported to the other processes as CUDA IPC handles.
+
+namespace {
+constexpr int P2P_SLOTS = 4, P2P_MAXW = 16;
+struct P2P {
+    double* mine[P2P_SLOTS] = { nullptr, nullptr, nullptr, nullptr };
+    size_t bytes[P2P_SLOTS] = { 0, 0, 0, 0 };
+    double* peer[P2P_SLOTS][P2P_MAXW] = {};
+    int rank = 0, world = 0;
+} X;
+}  // namespace
+
+int tkb_p2p_alloc(int slot, int64_t bytes, double** dev_ptr)
+{
+    if (slot < 0 || slot >= P2P_SLOTS || bytes <= 0 || !dev_ptr) return tkb::set_error("tkb_p2p_alloc: bad arguments");
+    if (X.mine[slot] && X.bytes[slot] != (size_t)bytes) {
+        if (X.world) return tkb::set_error("tkb_p2p_alloc: buffer is mapped by peers, call tkb_p2p_close first");
+        cudaFree(X.mine[slot]);
+        X.mine[slot] = nullptr;
+    }
+    if (!X.mine[slot]) {
+        const cudaError_t e = cudaMalloc(&X.mine[slot], (size_t)bytes);
+        if (e != cudaSuccess) return tkb::set_error(cudaGetErrorString(e));
+        X.bytes[slot] = (size_t)bytes;
+    }
+    *dev_ptr = X.mine[slot];
+    return 0;
+}
+
+int tkb_p2p_handle(int slot, char handle_out[64])
+{
+    if (slot < 0 || slot >= P2P_SLOTS || !X.mine[slot] || !handle_out) return tkb::set_error("tkb_p2p_handle: no buffer in this slot");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+    cudaIpcMemHandle_t h;
+    const cudaError_t e = cudaIpcGetMemHandle(&h, X.mine[slot]);
+    if (e != cudaSuccess) return tkb::set_error(cudaGetErrorString(e));
+    memcpy(handle_out, &h, 64);
+    return 0;
+}
+
+int tkb_p2p_open(int slot, int rank, int world, const char* handles_all)
+{
+    if (slot < 0 || slot >= P2P_SLOTS || world < 1 || world > P2P_MAXW || rank < 0 || rank >= world || !handles_all || !X.mine[slot])
+        return tkb::set_error("tkb_p2p_open: bad arguments");
+    for (int p = 0; p < world; p++) {
+        if (p == rank) { X.peer[slot][p] = X.mine[slot]; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles_all + (size_t)p * 64, 64);
+        void* ptr = nullptr;
+        const cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            char buf[256];
+            snprintf(buf, sizeof buf, "cudaIpcOpenMemHandle (rank %d -> buffer of rank %d): %s", rank, p, cudaGetErrorString(e));
+            return tkb::set_error(buf);
+        }
+        X.peer[slot][p] = (double*)ptr;
+    }
+    X.rank = rank;
+    X.world = world;
+    return 0;
+}
+
+int tkb_p2p_push_matrices(int slot, int type, int nstype, int k_first, void* stream)
+{
+    if (slot < 0 || slot >= P2P_SLOTS || !X.world || !X.peer[slot][X.rank] || k_first < 0)
+        return tkb::set_error("tkb_p2p_push_matrices: call tkb_p2p_alloc / tkb_p2p_open first");
+    const double* local = nullptr;
+    int64_t shape[4], strides[4];
+    if (tkb_evomatrix(type, nstype, &local, shape, strides)) return 1;
+    const int64_t m = shape[0], nxi = shape[2], nq2 = shape[3];
+    const size_t slab = (size_t)nq2 * (size_t)m * (size_t)m * sizeof(double);
+    if (((size_t)(k_first + nxi) * (size_t)X.world) * slab > X.bytes[slot])
+        return tkb::set_error("tkb_p2p_push_matrices: the receive buffer is too small for this chunk");
+    // local xi k -> position (k_first + k) * world + rank of every rank's buffer (own copy first)
+    for (int q = 0; q < X.world; q++) {
+        const int p = (X.rank + q) % X.world;
+        char* dst = (char*)X.peer[slot][p] + ((size_t)k_first * (size_t)X.world + (size_t)X.rank) * slab;
+        const cudaError_t e = cudaMemcpy2DAsync(dst, (size_t)X.world * slab, local, slab, slab, (size_t)nxi,
+                                                cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+        if (e != cudaSuccess) return tkb::set_error(cudaGetErrorString(e));
+    }
+    return 0;
+}
+
+int tkb_p2p_close(void)
+{
+    for (int s = 0; s < P2P_SLOTS; s++) {
+        for (int p = 0; p < X.world; p++)
+            if (p != X.rank && X.peer[s][p]) cudaIpcCloseMemHandle(X.peer[s][p]);
+        for (int p = 0; p < P2P_MAXW; p++) X.peer[s][p] = nullptr;
+        if (X.mine[s]) cudaFree(X.mine[s]);
+        X.mine[s] = nullptr;
+        X.bytes[s] = 0;
+    }
+    X.world = 0;
+    X.rank = 0;
+    return 0;
+}
+
 }  // extern "C"

@@ -28,6 +28,7 @@ int launch_compose(int n, int nxi, int nfl, const double* P, const double* diag,
                    cudaStream_t st);
 int launch_task_classes(int c, int npts, const double* xs, const double* ys, const double* xis, int* cls, double* full,
                         double* erbl, cudaStream_t st);
+int launch_eval_integrand(int c, int npts, const double* xs, const double* ys, const double* xis, double* out, cudaStream_t st);
 int launch_eval_kernels(int npts, const double* xs, const double* ys, const double* xis, double* out, cudaStream_t st);
 int launch_eval_scalar(int which, int npts, const double* a, const double* b, double* out, cudaStream_t st);
 

@@ -157,3 +157,53 @@ def gather_matrix_capi(name, counts, ns_type=1, out=None, layout="strided", k_fi
         cnt = (C.c_int * len(counts))(*[int(c) for c in counts])
         _lib.check(L.tkb_allgather_matrices(_MATRIX_TYPES[name], int(ns_type), cnt, C.c_void_p(out.data_ptr()), st))
     return out.permute(2, 3, 0, 1)
+
+
+# --------------------------------------------------------------------------------------------
+# the exchange by the copy engines (tkb_p2p_*): no NCCL kernel, no SMs, so it runs under the QAGS kernels of the next
+# chunk / step.  torch.distributed only carries the 64-byte CUDA IPC handles of the receive buffers.
+
+_P2P_SLOTS = {"matrix_VNS+": 0, "matrix_VNS-": 1, "matrix_VSG": 2, "matrix_ASG": 3}
+_P2P_FAMILY = {0: (0, 1), 1: (0, -1), 2: (1, 1), 3: (3, 1)}        # slot -> (tkb type, nstype)
+
+
+def init_p2p(nx, nxi_total, nq2, group=None):
+    """Allocate this rank's four receive buffers (VNS+, VNS-, VSG, ASG; [xi_total][Q2][m][m]) and map every peer's.
+    Returns the four buffers as tensors of logical shape (m, m, nxi_total, nQ2)."""
+    import ctypes as C
+    import torch.distributed as dist
+    from . import _lib
+    L = _lib.lib()
+    _lib.require_cuda()
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    views, handles = [], []
+    for slot in range(4):
+        m = nx * (2 if slot >= 2 else 1)
+        addr = C.c_void_p()
+        _lib.check(L.tkb_p2p_alloc(slot, int(nxi_total) * int(nq2) * m * m * 8, C.byref(addr)))
+        views.append(_lib.view_tensor(addr.value, (nxi_total, nq2, m, m)).permute(2, 3, 0, 1))
+        buf = C.create_string_buffer(64)
+        _lib.check(L.tkb_p2p_handle(slot, buf))
+        handles.append(buf.raw)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, handles, group=group)
+    for slot in range(4):
+        _lib.check(L.tkb_p2p_open(slot, rank, world, b"".join(gathered[r][slot] for r in range(world))))
+    return views
+
+
+def push_matrices_p2p(k_first=0, stream=None):
+    """Push this rank's current four matrix families into every rank's receive buffers (strided split: local xi k ->
+    global position (k_first + k) * world + rank).  Asynchronous on `stream` (default: the current stream); the
+    gathered arrays are complete once every rank's push has finished (dist.barrier after a stream synchronize)."""
+    import ctypes as C
+    from . import _lib
+    L = _lib.lib()
+    st = _lib.stream_ptr() if stream is None else C.c_void_p(stream.cuda_stream)
+    for slot, (t, ns) in _P2P_FAMILY.items():
+        _lib.check(L.tkb_p2p_push_matrices(slot, t, ns, int(k_first), st))
+
+
+def close_p2p():
+    from . import _lib
+    _lib.check(_lib.lib().tkb_p2p_close())

@@ -60,6 +60,22 @@ for n, ref in full_even.items():
     if not same:
         print("rank %d: chunked strided gather of %s differs" % (rank, n))
     ok = ok and same
+# the exchange by the copy engines (tkb_p2p_*): two chunks of one local xi each pushed into every rank's buffers
+views = tk.shard.init_p2p(nx, 2 * world, Q2.shape[0])
+for chunk in range(2):
+    mine_c = xi_even[rank::world][chunk:chunk + 1]
+    tk.shard.f90src.make_kernels_shard(nx, mine_c, gt, 0, 0)
+    tk.matrices.initialize_evolution_matrices(Q2, nlo=True)
+    tk.shard.push_matrices_p2p(k_first=chunk)
+torch.cuda.synchronize()
+dist.barrier()
+for slot, n in enumerate(("matrix_VNS", "matrix_ANS", "matrix_VSG", "matrix_ASG")):     # ANS(+1) is VNS(-1)
+    same = torch.equal(views[slot], full_even[n])
+    if not same:
+        print("rank %d: copy-engine exchange of %s differs" % (rank, n))
+    ok = ok and same
+dist.barrier()
+tk.shard.close_p2p()
 # bandwidth of the one exchange step at the bench's size (nx = 160, 256 xi per rank, Q2 4 -> 10): each rank
 # receives (world - 1) slabs of every matrix family over NVLink; device-timed, max over ranks
 if len(sys.argv) > 1 and sys.argv[1] == "--bw":
