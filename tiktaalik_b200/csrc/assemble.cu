@@ -61,7 +61,7 @@ TKB_DEV double node_eta(double centr, double hlgth, int q)
 }
 
 // ---------------------------------------------------------------------------------------
-// K1: fixed quadrature.  grid = (n, nxi), block = 256 threads.
+// K1: fixed quadrature.  grid = (ceil(n / K1_ROWS), nxi), block = 128 K1_ROWS threads, K1_ROWS rows (xi, i) per block.
 // P layout: P[f][ixi][i][j] (row-major n x n per xi).  diag layout: diag[ixi][i][DIAG_N].
 
 // One-argument logs / dilogs of the fixed point x_i (eval_half, FIX): the same for the 126 nodes of row (xi, i) in K1 and
@@ -88,242 +88,273 @@ __global__ void pre_table_kernel(int n, int nxi, const double* __restrict__ xi_a
     tab[e] = val;
 }
 
-constexpr int K1_THREADS = 256;
+#ifndef TKB_K1_ROWS
+#define TKB_K1_ROWS 4
+#endif
+constexpr int K1_ROWS = TKB_K1_ROWS;           // rows (xi, i) per block
+constexpr int K1_THREADS = 128 * K1_ROWS;
 constexpr int NNODE = 126;
 
-__global__ void __launch_bounds__(K1_THREADS, 2)
+// Shared memory of one block: K1_ROWS rows.  A row has 2 x 126 half-kernel tasks of which about half are live, i.e.
+// four warps' worth; with one row per block (round 1) the other four warps of the block waited at the barrier while
+// holding their 128 registers, so an SM had 8 live warps in the evaluation phase -- a latency-bound chain of several
+// thousand dependent instructions per task (ncu: 13 warps/SM, issue slots 34 % busy, barrier 2.9 and wait 3.0
+// warp-cycles per issue, 16.5 of 32 lanes active).  With K1_ROWS = 4 rows per 512-thread block every warp has live
+// tasks and the SM runs 16 of them.
+struct K1Shared {
+    double H[K1_ROWS][2][NKERN][NNODE];   // half-kernel values; after the combination pass [r][0][kernel][node] holds K(x_i, y_k)
+    double Y[K1_ROWS][NNODE][2];          // 0.5 (1 +- y/xi) at the nodes
+    double J[K1_ROWS][NNODE];             // Jacobians
+    double b[K1_ROWS][NNODE][6];          // basis rows at the nodes
+    double aa[K1_ROWS][8], hl[K1_ROWS][6], bx[K1_ROWS][6];
+    double pre[K1_ROWS][2][PRE_N];        // one-argument logs/dilogs of the row's fixed point (eval_half, FIX = 1)
+    double w[6];                          // Lagrange weights (the same for every row)
+    int iS[K1_ROWS][NNODE];               // stencil origins (1-based)
+    int iSx[K1_ROWS];
+    int allfinite[K1_ROWS];
+    int nlive;
+    unsigned short live[K1_ROWS * 2 * NNODE];
+};
+
+__global__ void __launch_bounds__(K1_THREADS, 1)
 assemble_fixed_kernel(int n, int nxi, const double* __restrict__ xi_arr, int grid_type,
                       double* __restrict__ P, double* __restrict__ diag)
 {
-    // half-kernel values [half][kernel][node]; after the combination pass [0][kernel][node] holds K(x_i, y_k)
-    extern __shared__ __align__(16) double s_dyn[];
-    double (*s_H)[NKERN][NNODE] = reinterpret_cast<double (*)[NKERN][NNODE]>(s_dyn);
-    double (*s_K)[NNODE] = s_H[0];
-    __shared__ double s_Y[NNODE][2];          // 0.5 (1 +- y/xi) at the nodes
-    __shared__ unsigned char s_live[2 * NNODE];
-    __shared__ int s_nlive;
-    __shared__ double s_J[NNODE];             // Jacobians
-    __shared__ double s_b[NNODE][6];          // basis rows at the nodes
-    __shared__ int s_iS[NNODE];               // stencil origins (1-based)
-    __shared__ double s_aa[8], s_hl[6], s_w[6], s_bx[6];
-    __shared__ int s_iSx;
-    __shared__ int s_allfinite;
-    __shared__ double s_pre[2][PRE_N];        // one-argument logs/dilogs of the row's fixed point (eval_half, FIX = 1)
-
-    const int i = blockIdx.x + 1;             // 1-based row
-    const int ixi = blockIdx.y;
+    extern __shared__ __align__(16) unsigned char k1_smem[];
+    K1Shared& sh = *reinterpret_cast<K1Shared*>(k1_smem);
     const int tid = threadIdx.x;
+    const int ixi = blockIdx.y;
+    const int i0 = blockIdx.x * K1_ROWS;           // 0-based first row of the block
+    const int nrows = (n - i0 < K1_ROWS) ? (n - i0) : K1_ROWS;
     const double xi = xi_arr[ixi];
-    const double* rowtab = d_pre_tab + ((size_t)ixi * n + (size_t)(i - 1)) * PRE_ROW;   // filled by pre_table_kernel
-    const double x = rowtab[PRE_X];
+    const double* tab0 = d_pre_tab + ((size_t)ixi * n + (size_t)i0) * PRE_ROW;   // filled by pre_table_kernel
 
     // set-up, spread over a few threads of different warps (every piece is a chain of dependent log / pow / divisions):
     // integration.f90:27-35 breakpoints in eta space; Lagrange weights; eta of x_i; the row's one-argument logs/dilogs
-    if (tid < 7) {
-        const double ax = fabs(x), axi = fabs(xi);
-        const double arg = (tid == 0) ? -1.0 : (tid == 1) ? -ax : (tid == 2) ? -axi : (tid == 3) ? 0.0
-                         : (tid == 4) ? axi : (tid == 5) ? ax : 1.0;
-        s_aa[tid + 1] = pull_back(arg, xi, grid_type);
-    } else if (tid == 32) {
-        double w[6];
-        lagrange_weights(n, w);
-        for (int m = 0; m < 6; m++) s_w[m] = w[m];
-    } else if (tid == 64) {
-        s_aa[0] = pull_back(x, xi, grid_type);                 // eta of x_i, for the basis row below
-        s_allfinite = 1;
-    } else if (tid >= 96 && tid < 96 + 2 * PRE_N) {
-        const int v = tid - 96;
-        s_pre[v / PRE_N][v % PRE_N] = rowtab[v];
+    {
+        const int r = tid >> 7, t = tid & 127;      // 128 threads per row
+        if (r < nrows) {
+            const double* rowtab = tab0 + (size_t)r * PRE_ROW;
+            const double x = rowtab[PRE_X];
+            if (t < 7) {
+                const double ax = fabs(x), axi = fabs(xi);
+                const double arg = (t == 0) ? -1.0 : (t == 1) ? -ax : (t == 2) ? -axi : (t == 3) ? 0.0
+                                 : (t == 4) ? axi : (t == 5) ? ax : 1.0;
+                sh.aa[r][t + 1] = pull_back(arg, xi, grid_type);
+            } else if (t == 32 && r == 0) {
+                double w[6];
+                lagrange_weights(n, w);
+                for (int m = 0; m < 6; m++) sh.w[m] = w[m];
+            } else if (t == 64) {
+                sh.aa[r][0] = pull_back(x, xi, grid_type);             // eta of x_i, for the basis row below
+                sh.allfinite[r] = 1;
+            } else if (t >= 96 && t < 96 + 2 * PRE_N) {
+                const int v = t - 96;
+                sh.pre[r][v / PRE_N][v % PRE_N] = rowtab[v];
+            }
+        }
+        if (tid == 0) sh.nlive = 0;
     }
     __syncthreads();
-    if (tid == 0) {
-        double aa[8];
-        for (int r = 1; r <= 7; r++) aa[r] = s_aa[r];
-        if (aa[3] < aa[2]) { const double z = aa[2]; aa[2] = aa[3]; aa[3] = z; }      // inner pairs sorted
-        if (aa[6] < aa[5]) { const double z = aa[5]; aa[5] = aa[6]; aa[6] = z; }
-        for (int r = 1; r <= 7; r++) s_aa[r] = aa[r];
-        for (int r = 0; r < 6; r++) s_hl[r] = 5.0e-01 * (aa[r + 2] - aa[r + 1]);
-    } else if (tid == 32) {
-        // basis row at x_i itself (interpixel(j, x): pull_back then Lagrange, convolution.f90:77,93)
-        double w[6], bx[6];
-        for (int m = 0; m < 6; m++) w[m] = s_w[m];
-        s_iSx = basis_row(s_aa[0], n, w, bx);
-        for (int m = 0; m < 6; m++) s_bx[m] = bx[m];
+    {
+        const int r = tid >> 7, t = tid & 127;
+        if (r < nrows) {
+            if (t == 0) {
+                double aa[8];
+                for (int q = 1; q <= 7; q++) aa[q] = sh.aa[r][q];
+                if (aa[3] < aa[2]) { const double z = aa[2]; aa[2] = aa[3]; aa[3] = z; }      // inner pairs sorted
+                if (aa[6] < aa[5]) { const double z = aa[5]; aa[5] = aa[6]; aa[6] = z; }
+                for (int q = 1; q <= 7; q++) sh.aa[r][q] = aa[q];
+                for (int q = 0; q < 6; q++) sh.hl[r][q] = 5.0e-01 * (aa[q + 2] - aa[q + 1]);
+            } else if (t == 32) {
+                // basis row at x_i itself (interpixel(j, x): pull_back then Lagrange, convolution.f90:77,93)
+                double w[6], bx[6];
+                for (int m = 0; m < 6; m++) w[m] = sh.w[m];
+                sh.iSx[r] = basis_row(sh.aa[r][0], n, w, bx);
+                for (int m = 0; m < 6; m++) sh.bx[r][m] = bx[m];
+            }
+        }
     }
     __syncthreads();
 
-    // ---- phase 1a: one thread per (node, half): node, Jacobian / basis row, support class of the half ----
+    // ---- phase 1a: one thread per (row, node, half): node, Jacobian / basis row, support class of the half ----
     // A half kernel whose support steps rho and theta_ERBL both vanish is an exact zero when every skipped piece
     // is finite (node_is_safe, as in K2); such halves -- about half of them -- are not evaluated, and the live
     // ones are compacted so that whole warps drop out of the evaluation pass.
-    if (tid == 0) s_nlive = 0;
-    __syncthreads();
-    {
-        const int k = tid >> 1, half = tid & 1;
-        if (k < NNODE) {
-            const int r = k / 21, q = k - 21 * r;
-            const double a = s_aa[r + 1], b = s_aa[r + 2];
-            const double centr = 5.0e-01 * (a + b);
-            const double hlgth = 5.0e-01 * (b - a);
-            const double eta = node_eta(centr, hlgth, q);
-            const double y = push_forward(eta, xi, grid_type);
-            if (half == 0) {
-                s_J[k] = push_jacob(eta, xi, grid_type);
-            } else {
-                double w[6], bb[6];
+    for (int e = tid; e < nrows * 2 * NNODE; e += K1_THREADS) {
+        const int r = e / (2 * NNODE), t = e - r * 2 * NNODE;
+        const int k = t >> 1, half = t & 1;
+        const double* rowtab = tab0 + (size_t)r * PRE_ROW;
+        const int iv = k / 21, q = k - 21 * iv;
+        const double a = sh.aa[r][iv + 1], b = sh.aa[r][iv + 2];
+        const double centr = 5.0e-01 * (a + b);
+        const double hlgth = 5.0e-01 * (b - a);
+        const double eta = node_eta(centr, hlgth, q);
+        const double y = push_forward(eta, xi, grid_type);
+        if (half == 0) {
+            sh.J[r][k] = push_jacob(eta, xi, grid_type);
+        } else {
+            double w[6], bb[6];
 #pragma unroll
-                for (int m = 0; m < 6; m++) w[m] = s_w[m];
-                s_iS[k] = basis_row(pull_back(y, xi, grid_type), n, w, bb);
+            for (int m = 0; m < 6; m++) w[m] = sh.w[m];
+            sh.iS[r][k] = basis_row(pull_back(y, xi, grid_type), n, w, bb);
 #pragma unroll
-                for (int m = 0; m < 6; m++) s_b[k][m] = bb[m];
-            }
-            const double X1 = rowtab[PRE_U1], X2 = rowtab[PRE_U2];
-            const double Y1 = 0.5 * (1.0 + y / xi), Y2 = 0.5 * (1.0 - y / xi);
-            if (half == 0) { s_Y[k][0] = Y1; s_Y[k][1] = Y2; }
-            const bool safe = node_is_safe(X1, X2, Y1, Y2);
-            const int cls = half ? task_class(X2, Y2, safe) : task_class(X1, Y1, safe);
-            if (cls != 0) {
-                s_live[atomicAdd(&s_nlive, 1)] = (unsigned char)tid;
-            } else {
+            for (int m = 0; m < 6; m++) sh.b[r][k][m] = bb[m];
+        }
+        const double X1 = rowtab[PRE_U1], X2 = rowtab[PRE_U2];
+        const double Y1 = 0.5 * (1.0 + y / xi), Y2 = 0.5 * (1.0 - y / xi);
+        if (half == 0) { sh.Y[r][k][0] = Y1; sh.Y[r][k][1] = Y2; }
+        const bool safe = node_is_safe(X1, X2, Y1, Y2);
+        const int cls = half ? task_class(X2, Y2, safe) : task_class(X1, Y1, safe);
+        if (cls != 0) {
+            sh.live[atomicAdd(&sh.nlive, 1)] = (unsigned short)e;
+        } else {
 #pragma unroll
-                for (int f = 0; f < NKERN; f++) s_H[half][f][k] = 0.0;
-            }
+            for (int f = 0; f < NKERN; f++) sh.H[r][half][f][k] = 0.0;
         }
     }
     __syncthreads();
     // ---- phase 1b: the live halves, all 22 kernels each ----
     {
-        const int nlive = s_nlive;
+        const int nlive = sh.nlive;
         for (int idx = tid; idx < nlive; idx += K1_THREADS) {
-            const int task = s_live[idx];
-            const int k = task >> 1, half = task & 1;
+            const int e = sh.live[idx];
+            const int r = e / (2 * NNODE), t = e - r * 2 * NNODE;
+            const int k = t >> 1, half = t & 1;
+            const double* rowtab = tab0 + (size_t)r * PRE_ROW;
             const double X1 = rowtab[PRE_U1], X2 = rowtab[PRE_U2];
-            const double Y1 = s_Y[k][0], Y2 = s_Y[k][1];
+            const double Y1 = sh.Y[r][k][0], Y2 = sh.Y[r][k][1];
             double hv[NKERN];
-            if (half == 0) eval_half<MASK_ALL, true, 1>(X1, Y1, X2, Y2, hv, s_pre[0], s_pre[1]);
-            else eval_half<MASK_ALL, true, 1>(X2, Y2, X1, Y1, hv, s_pre[1], s_pre[0]);
+            if (half == 0) eval_half<MASK_ALL, true, 1>(X1, Y1, X2, Y2, hv, sh.pre[r][0], sh.pre[r][1]);
+            else eval_half<MASK_ALL, true, 1>(X2, Y2, X1, Y1, hv, sh.pre[r][1], sh.pre[r][0]);
 #pragma unroll
-            for (int f = 0; f < NKERN; f++) s_H[half][f][k] = hv[f];
+            for (int f = 0; f < NKERN; f++) sh.H[r][half][f][k] = hv[f];
         }
     }
     __syncthreads();
     // ---- phase 1c: K(x_i, y_k) from the two halves, in place ----
-    if (tid < NNODE) {
-        const int k = tid;
+    for (int e = tid; e < nrows * NNODE; e += K1_THREADS) {
+        const int r = e / NNODE, k = e - r * NNODE;
         bool fin = true;
 #pragma unroll
         for (int f = 0; f < NKERN; f++) {
-            const double K = combine_halves_rt(f, s_H[0][f][k], s_H[1][f][k], xi);
-            s_K[f][k] = K;
+            const double K = combine_halves_rt(f, sh.H[r][0][f][k], sh.H[r][1][f][k], xi);
+            sh.H[r][0][f][k] = K;
             fin = fin && (fabs(K) <= huge_());
         }
-        if (!(fin && fabs(s_J[k]) <= huge_())) s_allfinite = 0;
+        if (!(fin && fabs(sh.J[r][k]) <= huge_())) sh.allfinite[r] = 0;
     }
     __syncthreads();
 
-    // ---- phase 2: one thread per column j; replay qk21 per interval in the reference's order ----
-    const bool dense = (s_allfinite == 0);     // a NaN/Inf kernel value poisons every column (0*NaN)
-    const int iSx = s_iSx;
-    const size_t rowbase = ((size_t)ixi * n + (size_t)(i - 1)) * n;
+    // ---- phase 2: one thread per (row, column j); replay qk21 per interval in the reference's order ----
     const size_t fstride = (size_t)nxi * n * n;
     // The six columns whose basis function is non-zero at x_i carry the subtraction term f_j(x_i) of the plus
     // kernels at every node (66 accumulation steps instead of the ~4 of an ordinary column).  They are split
-    // by kernel, one thread per (column, kernel), so that no thread walks all nodes for all 22 kernels.
-    if (!dense && tid < 6 * NKERN) {
-        const int jh = tid / NKERN, f = tid - NKERN * jh;
-        const int j = iSx + jh;
-        const double fx = s_bx[jh];
-        if (fx != 0.0) {
-            const bool plus = is_plus(f);
-            double integral = 0.0;
-            for (int r = 0; r < 6; r++) {
-                double resk = 0.0;
-                for (int s = 0; s <= 10; s++) {
-                    const int t = (s == 0) ? 11 : ((s <= 5) ? 2 * s : 2 * (s - 5) - 1);
-                    const int k1 = 21 * r + ((s == 0) ? 0 : 2 * t - 1);
-                    const int k2 = k1 + 1;
-                    const int m1 = j - s_iS[k1];
-                    const bool in1 = (m1 >= 0 && m1 < 6);
-                    bool in2 = false;
-                    int m2 = 0;
-                    if (s != 0) { m2 = j - s_iS[k2]; in2 = (m2 >= 0 && m2 < 6); }
-                    if (!(plus || in1 || in2)) continue;
-                    const double fy1 = in1 ? s_b[k1][m1] : 0.0;
-                    const double J1 = s_J[k1];
-                    const double w = c_wgk[t];
-                    if (s == 0) {
-                        const double fc = plus ? (s_K[f][k1] * (fy1 - fx)) * J1 : (s_K[f][k1] * fy1) * J1;
-                        resk = w * fc;
-                    } else {
-                        const double fy2 = in2 ? s_b[k2][m2] : 0.0;
-                        const double J2 = s_J[k2];
-                        const double v1 = plus ? (s_K[f][k1] * (fy1 - fx)) * J1 : (s_K[f][k1] * fy1) * J1;
-                        const double v2 = plus ? (s_K[f][k2] * (fy2 - fx)) * J2 : (s_K[f][k2] * fy2) * J2;
-                        const double fsum = v1 + v2;
-                        resk = resk + w * fsum;
-                    }
+    // by kernel, one thread per (row, column, kernel), so that no thread walks all nodes for all 22 kernels.
+    for (int e = tid; e < nrows * 6 * NKERN; e += K1_THREADS) {
+        const int r = e / (6 * NKERN), t = e - r * 6 * NKERN;
+        if (sh.allfinite[r] == 0) continue;            // a NaN/Inf kernel value poisons every column (0*NaN): dense pass below
+        const int jh = t / NKERN, f = t - NKERN * jh;
+        const int j = sh.iSx[r] + jh;
+        const double fx = sh.bx[r][jh];
+        if (fx == 0.0) continue;
+        const double (*sK)[NNODE] = sh.H[r][0];
+        const bool plus = is_plus(f);
+        double integral = 0.0;
+        for (int iv = 0; iv < 6; iv++) {
+            double resk = 0.0;
+            for (int s = 0; s <= 10; s++) {
+                const int tt = (s == 0) ? 11 : ((s <= 5) ? 2 * s : 2 * (s - 5) - 1);
+                const int k1 = 21 * iv + ((s == 0) ? 0 : 2 * tt - 1);
+                const int k2 = k1 + 1;
+                const int m1 = j - sh.iS[r][k1];
+                const bool in1 = (m1 >= 0 && m1 < 6);
+                bool in2 = false;
+                int m2 = 0;
+                if (s != 0) { m2 = j - sh.iS[r][k2]; in2 = (m2 >= 0 && m2 < 6); }
+                if (!(plus || in1 || in2)) continue;
+                const double fy1 = in1 ? sh.b[r][k1][m1] : 0.0;
+                const double J1 = sh.J[r][k1];
+                const double w = c_wgk[tt];
+                if (s == 0) {
+                    const double fc = plus ? (sK[f][k1] * (fy1 - fx)) * J1 : (sK[f][k1] * fy1) * J1;
+                    resk = w * fc;
+                } else {
+                    const double fy2 = in2 ? sh.b[r][k2][m2] : 0.0;
+                    const double J2 = sh.J[r][k2];
+                    const double v1 = plus ? (sK[f][k1] * (fy1 - fx)) * J1 : (sK[f][k1] * fy1) * J1;
+                    const double v2 = plus ? (sK[f][k2] * (fy2 - fx)) * J2 : (sK[f][k2] * fy2) * J2;
+                    const double fsum = v1 + v2;
+                    resk = resk + w * fsum;
                 }
-                integral = integral + resk * s_hl[r];
             }
-            P[(size_t)f * fstride + rowbase + (size_t)(j - 1)] = integral;
+            integral = integral + resk * sh.hl[r][iv];
         }
+        P[(size_t)f * fstride + ((size_t)ixi * n + (size_t)(i0 + r)) * n + (size_t)(j - 1)] = integral;
     }
-    for (int j = tid + 1; j <= n; j += K1_THREADS) {
+    for (int e = tid; e < nrows * n; e += K1_THREADS) {
+        const int r = e / n, j = e - r * n + 1;
+        const bool dense = (sh.allfinite[r] == 0);
+        const int iSx = sh.iSx[r];
         const int mx = j - iSx;
-        const double fx = (mx >= 0 && mx < 6) ? s_bx[mx] : 0.0;
+        const double fx = (mx >= 0 && mx < 6) ? sh.bx[r][mx] : 0.0;
         if (!dense && fx != 0.0) continue;                     // done above, one thread per kernel
+        const double (*sK)[NNODE] = sh.H[r][0];
         double integral[NKERN];
 #pragma unroll
         for (int f = 0; f < NKERN; f++) integral[f] = 0.0;
-        for (int r = 0; r < 6; r++) {
+        for (int iv = 0; iv < 6; iv++) {
             double resk[NKERN];
 #pragma unroll
             for (int f = 0; f < NKERN; f++) resk[f] = 0.0;
             // qk21 order: centre (weight wgk(11)), then t = 2,4,..,10, then t = 1,3,..,9
             for (int s = 0; s <= 10; s++) {
-                const int t = (s == 0) ? 11 : ((s <= 5) ? 2 * s : 2 * (s - 5) - 1);
-                const int k1 = 21 * r + ((s == 0) ? 0 : 2 * t - 1);
+                const int tt = (s == 0) ? 11 : ((s <= 5) ? 2 * s : 2 * (s - 5) - 1);
+                const int k1 = 21 * iv + ((s == 0) ? 0 : 2 * tt - 1);
                 const int k2 = k1 + 1;                       // unused for the centre
-                const int m1 = j - s_iS[k1];
+                const int m1 = j - sh.iS[r][k1];
                 const bool in1 = (m1 >= 0 && m1 < 6);
                 bool in2 = false;
                 int m2 = 0;
-                if (s != 0) { m2 = j - s_iS[k2]; in2 = (m2 >= 0 && m2 < 6); }
+                if (s != 0) { m2 = j - sh.iS[r][k2]; in2 = (m2 >= 0 && m2 < 6); }
                 if (!(dense || in1 || in2 || fx != 0.0)) continue;
-                const double fy1 = in1 ? s_b[k1][m1] : 0.0;
-                const double J1 = s_J[k1];
-                const double w = c_wgk[t];
+                const double fy1 = in1 ? sh.b[r][k1][m1] : 0.0;
+                const double J1 = sh.J[r][k1];
+                const double w = c_wgk[tt];
                 if (s == 0) {
 #pragma unroll
                     for (int f = 0; f < NKERN; f++) {
-                        const double fc = is_plus(f) ? (s_K[f][k1] * (fy1 - fx)) * J1 : (s_K[f][k1] * fy1) * J1;
+                        const double fc = is_plus(f) ? (sK[f][k1] * (fy1 - fx)) * J1 : (sK[f][k1] * fy1) * J1;
                         resk[f] = w * fc;
                     }
                 } else {
-                    const double fy2 = in2 ? s_b[k2][m2] : 0.0;
-                    const double J2 = s_J[k2];
+                    const double fy2 = in2 ? sh.b[r][k2][m2] : 0.0;
+                    const double J2 = sh.J[r][k2];
 #pragma unroll
                     for (int f = 0; f < NKERN; f++) {
-                        const double v1 = is_plus(f) ? (s_K[f][k1] * (fy1 - fx)) * J1 : (s_K[f][k1] * fy1) * J1;
-                        const double v2 = is_plus(f) ? (s_K[f][k2] * (fy2 - fx)) * J2 : (s_K[f][k2] * fy2) * J2;
+                        const double v1 = is_plus(f) ? (sK[f][k1] * (fy1 - fx)) * J1 : (sK[f][k1] * fy1) * J1;
+                        const double v2 = is_plus(f) ? (sK[f][k2] * (fy2 - fx)) * J2 : (sK[f][k2] * fy2) * J2;
                         const double fsum = v1 + v2;
                         resk[f] = resk[f] + w * fsum;
                     }
                 }
             }
-            const double hl = s_hl[r];
+            const double hl = sh.hl[r][iv];
 #pragma unroll
             for (int f = 0; f < NKERN; f++) integral[f] = integral[f] + resk[f] * hl;
         }
+        const size_t rowbase = ((size_t)ixi * n + (size_t)(i0 + r)) * n;
 #pragma unroll
         for (int f = 0; f < NKERN; f++) P[(size_t)f * fstride + rowbase + (size_t)(j - 1)] = integral[f];
     }
 
     // ---- diagonal bookkeeping: f_i(x_i) and the analytic LO constants ----
-    if (tid == 0) {
+    if ((tid & 127) == 0 && (tid >> 7) < nrows) {
+        const int r = tid >> 7, i = i0 + r + 1;
+        const double x = tab0[(size_t)r * PRE_ROW + PRE_X];
         double* d = diag + ((size_t)ixi * n + (size_t)(i - 1)) * DIAG_N;
-        const int mi = i - iSx;
-        d[DIAG_FX] = (mi >= 0 && mi < 6) ? s_bx[mi] : 0.0;
+        const int mi = i - sh.iSx[r];
+        d[DIAG_FX] = (mi >= 0 && mi < 6) ? sh.bx[r][mi] : 0.0;
         d[DIAG_X] = x;
         d[DIAG_K0QQ] = K0_qq_cst(x, xi);
         d[DIAG_A0GG] = KA0_GG_cst(x, xi);
@@ -881,8 +912,8 @@ int set_grid_variant(int eta_recip_f32, int x0_recip_f32)
 
 int launch_assemble_fixed(int n, int nxi, const double* xi_dev, int grid_type, double* P, double* diag, cudaStream_t st)
 {
-    dim3 grid(n, nxi);
-    const size_t smem = 2 * sizeof(double) * NKERN * NNODE;
+    dim3 grid((n + K1_ROWS - 1) / K1_ROWS, nxi);
+    const size_t smem = sizeof(K1Shared);
     cudaError_t e = cudaFuncSetAttribute(assemble_fixed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
     assemble_fixed_kernel<<<grid, K1_THREADS, smem, st>>>(n, nxi, xi_dev, grid_type, P, diag);
