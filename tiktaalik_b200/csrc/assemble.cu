@@ -214,21 +214,46 @@ assemble_fixed_kernel(int n, int nxi, const double* __restrict__ xi_arr, int gri
         }
     }
     __syncthreads();
-    // ---- phase 1b: the live halves, all 22 kernels each ----
+    // ---- phase 1b: the live halves, all 22 kernels each, in eight passes of two or three kernels ----
+    // One evaluation of all 22 kernels is ~100 KB of straight-line code; as a single pass every warp streamed it from
+    // L2 on its own (the warps drift apart by more than the instruction cache holds).  Here the transcendental values
+    // of the node, which all kernels share, are computed first (node_values: small hot code), then the kernels follow
+    // group by group with a block barrier between the groups, so that the 16 warps run the same ~10 KB of formulas at
+    // the same time.  Values and formulas are those of the single pass: bit-identical results.
     {
         const int nlive = sh.nlive;
-        for (int idx = tid; idx < nlive; idx += K1_THREADS) {
-            const int e = sh.live[idx];
+        for (int base = 0; base < nlive; base += K1_THREADS) {
+            const int idx = base + tid;
+            const bool active = idx < nlive;
+            const int e = active ? sh.live[idx] : 0;
             const int r = e / (2 * NNODE), t = e - r * 2 * NNODE;
             const int k = t >> 1, half = t & 1;
             const double* rowtab = tab0 + (size_t)r * PRE_ROW;
             const double X1 = rowtab[PRE_U1], X2 = rowtab[PRE_U2];
             const double Y1 = sh.Y[r][k][0], Y2 = sh.Y[r][k][1];
-            double hv[NKERN];
-            if (half == 0) eval_half<MASK_ALL, true, 1>(X1, Y1, X2, Y2, hv, sh.pre[r][0], sh.pre[r][1]);
-            else eval_half<MASK_ALL, true, 1>(X2, Y2, X1, Y1, hv, sh.pre[r][1], sh.pre[r][0]);
-#pragma unroll
-            for (int f = 0; f < NKERN; f++) sh.H[r][half][f][k] = hv[f];
+            const double X = half ? X2 : X1, Y = half ? Y2 : Y1, Xo = half ? X1 : X2, Yo = half ? Y1 : Y2;
+            const double* preS = sh.pre[r][half];
+            const double* preO = sh.pre[r][half ^ 1];
+            double tv[TV_N];
+            if (active) node_values(X, Y, Xo, tv);
+#define TKB_K1_GROUP(MASK)                                                                   \
+            __syncthreads();                                                                  \
+            if (active) {                                                                     \
+                double hv[NKERN];                                                             \
+                eval_half<(MASK), true, 4>(X, Y, Xo, Yo, hv, preS, preO, 0, tv);              \
+                _Pragma("unroll")                                                             \
+                for (int f = 0; f < NKERN; f++)                                               \
+                    if ((MASK) & bit(f)) sh.H[r][half][f][k] = hv[f];                         \
+            }
+            TKB_K1_GROUP(0x7fu | bit(K_NSN))                   // the seven LO kernels and the nfl part of the non-singlet one
+            TKB_K1_GROUP(bit(K_NSP) | bit(K_NSM))
+            TKB_K1_GROUP(bit(K_V1QQ) | bit(K_A1QQ))
+            TKB_K1_GROUP(bit(K_V1QG) | bit(K_A1QG))
+            TKB_K1_GROUP(bit(K_V1GQ) | bit(K_V1GQN))
+            TKB_K1_GROUP(bit(K_A1GQ) | bit(K_A1GQN))
+            TKB_K1_GROUP(bit(K_V1GG) | bit(K_V1GGN))
+            TKB_K1_GROUP(bit(K_A1GG) | bit(K_A1GGN))
+#undef TKB_K1_GROUP
         }
     }
     __syncthreads();

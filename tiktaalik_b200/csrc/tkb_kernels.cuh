@@ -318,13 +318,36 @@ TKB_DEV double pre_value(int which, double U)
     return (which >= PRE_D) ? dilog(arg) : abslog(arg);
 }
 
+// FIX = 4 (the fixed-quadrature kernel, which evaluates the 22 kernels of a node in several passes of a few kernels
+// each): X belongs to the fixed point as with FIX = 1, and the transcendental values that depend on the node -- the
+// same for every kernel -- were computed once by node_values() and are passed in `tv`.
+enum { TV_LR = 0, TV_LOMR, TV_LYX1, TV_LY, TV_DYB, TV_GD, TV_GDO, TV_N };
+
+// exactly the expressions eval_half uses for these values (same operations, same order)
+TKB_DEV void node_values(double X, double Y, double Xo, double* __restrict__ tv)
+{
+    const double Xb = 1.0 - X, Yb = 1.0 - Y;
+    const double r = X / Y;
+    const double omr = 1.0 - r;
+    const double yx1 = Y / X - 1.0;
+    tv[TV_LR] = abslog(r);
+    tv[TV_LOMR] = abslog(omr);
+    tv[TV_LYX1] = abslog(yx1);
+    tv[TV_LY] = abslog(Y);
+    tv[TV_DYB] = dilog(Yb);
+    tv[TV_GD] = dilog(1.0 - Xb / Y);
+    tv[TV_GDO] = dilog(1.0 - Xo / Y);
+}
+
 template <unsigned MASK, bool WITH_RHO = true, int FIX = 0>
 __device__ __forceinline__ void eval_half(double X, double Y, double Xo, double Yo, double* __restrict__ out,
                                           const double* __restrict__ preS = nullptr,
-                                          const double* __restrict__ preO = nullptr, int fix_rt = 0)
+                                          const double* __restrict__ preO = nullptr, int fix_rt = 0,
+                                          const double* __restrict__ tv = nullptr)
 {
     // FIX = 3: the side of the fixed point is a run-time (warp-uniform) argument, one copy of the formulas serves both
-    const bool F1 = (FIX == 1) || (FIX == 3 && fix_rt == 1);
+    constexpr bool TV = (FIX == 4);
+    const bool F1 = (FIX == 1) || TV || (FIX == 3 && fix_rt == 1);
     const bool F2 = (FIX == 2) || (FIX == 3 && fix_rt == 2);
     static_assert(WITH_RHO || (MASK & ~MASK_QAGS) == 0, "erbl-only evaluation exists for the QAGS kernels only");
     constexpr bool LO_ANY = (MASK & 0x7fu) != 0;
@@ -355,14 +378,14 @@ __device__ __forceinline__ void eval_half(double X, double Y, double Xo, double 
     const double erbl = theta_step(X) * theta_step(Xb);
 
     double lr = 0, lomr = 0, lyx1 = 0, yx1 = 0, lX = 0, lXb = 0, lY = 0, DX = 0, DYb = 0, DXb = 0;
-    if (N_lr) lr = abslog(r);
-    if (N_lomr) lomr = abslog(omr);
-    if (N_lyx1) { yx1 = Y / X - 1.0; lyx1 = abslog(yx1); }
+    if (N_lr) lr = TV ? tv[TV_LR] : abslog(r);
+    if (N_lomr) lomr = TV ? tv[TV_LOMR] : abslog(omr);
+    if (N_lyx1) { yx1 = Y / X - 1.0; lyx1 = TV ? tv[TV_LYX1] : abslog(yx1); }
     if (N_lX) lX = F1 ? preS[PRE_L] : abslog(X);
     if (N_lXb) lXb = F1 ? preS[PRE_LB] : abslog(Xb);
-    if (N_lY) lY = F2 ? preS[PRE_L] : abslog(Y);
+    if (N_lY) lY = TV ? tv[TV_LY] : (F2 ? preS[PRE_L] : abslog(Y));
     if (N_DX) DX = F1 ? preS[PRE_D] : dilog(X);
-    if (N_DYb) DYb = F2 ? preS[PRE_DB] : dilog(Yb);
+    if (N_DYb) DYb = TV ? tv[TV_DYB] : (F2 ? preS[PRE_DB] : dilog(Yb));
     if (N_DXb) DXb = F1 ? preS[PRE_DB] : dilog(Xb);
     const double L2r = sqlog(lr, r);                      // log2(X/Y)
     const double L2X = sqlog(lX, X);                      // log2(X)
@@ -372,7 +395,7 @@ __device__ __forceinline__ void eval_half(double X, double Y, double Xo, double 
     double G = 0, DXbb = 0, Xbb = 0;
     if (HV && WITH_RHO) {
         Xbb = 1.0 - Xb;
-        G = 2.0 * dilog(1.0 - Xb / Y) + sqlog(lY, Y);
+        G = 2.0 * (TV ? tv[TV_GD] : dilog(1.0 - Xb / Y)) + sqlog(lY, Y);
         DXbb = F1 ? preS[PRE_DBB] : dilog(Xbb);
     }
 
@@ -406,7 +429,7 @@ __device__ __forceinline__ void eval_half(double X, double Y, double Xo, double 
                 const double QQh = h_pp(QQf, qq_fab(Xb, Yb), LPXbY, DS);
                 // QQ_hbar(Xo, Y): its X is Xo, its Xbar is 1 - Xo
                 const double Xob = 1.0 - Xo;
-                const double Go = 2.0 * dilog(1.0 - Xo / Y) + sqlog(lY, Y);
+                const double Go = 2.0 * (TV ? tv[TV_GDO] : dilog(1.0 - Xo / Y)) + sqlog(lY, Y);
                 const double QQhbar = hbar_pp(qq_fab(Xo, Y), qq_fab(Xob, Yb), Go, DYb, prodlog(lXo, Xo, lY, Y),
                                                F1 ? preO[PRE_DB] : dilog(Xob));
                 const double beta0 = -R11_3 * CA;
