@@ -16,6 +16,7 @@
 #include <dlfcn.h>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 
 #include "../../include/tiktaalik_b200.h"
 #include "tkb_internal.h"
@@ -232,6 +233,15 @@ int tkb_p2p_open(int slot, int rank, int world, const char* handles_all)
     return 0;
 }
 
+static int p2p_mode_kernel()
+{
+    // default: pitched peer copies by the driver / copy engines; TKB_P2P_COPY=kernel: exchange.cu's peer-store kernel
+    // (measured on 8 B200, C3: 147.5 ms per step with the copies, 154.2 ms with the kernel, which takes issue slots and
+    // memory bandwidth from the QAGS kernels it runs beside and reaches 510 GB/s alone against 675 GB/s)
+    static const int v = [] { const char* e = getenv("TKB_P2P_COPY"); return (e && e[0] == 'k') ? 1 : 0; }();
+    return v;
+}
+
 int tkb_p2p_push_matrices(int slot, int type, int nstype, int k_first, void* stream)
 {
     if (slot < 0 || slot >= P2P_SLOTS || !X.world || !X.peer[slot][X.rank] || k_first < 0)
@@ -244,6 +254,8 @@ int tkb_p2p_push_matrices(int slot, int type, int nstype, int k_first, void* str
     if (((size_t)(k_first + nxi) * (size_t)X.world) * slab > X.bytes[slot])
         return tkb::set_error("tkb_p2p_push_matrices: the receive buffer is too small for this chunk");
     // local xi k -> position (k_first + k) * world + rank of every rank's buffer (own copy first)
+    if (p2p_mode_kernel())
+        return tkb::launch_push_slabs(local, X.peer[slot], slab / sizeof(double), (int)nxi, X.world, X.rank, k_first, (cudaStream_t)stream);
     for (int q = 0; q < X.world; q++) {
         const int p = (X.rank + q) % X.world;
         char* dst = (char*)X.peer[slot][p] + ((size_t)k_first * (size_t)X.world + (size_t)X.rank) * slab;

@@ -59,6 +59,10 @@ int launch_evolve_fixed_flavor(int n, int nxi, int nq, int64_t S, int nfl, int F
 int launch_apply(int m, int nxi, int nq2, int64_t S, const double* M, const double* g, int64_t ldg, int64_t xig,
                  double* out, cudaStream_t st);
 
+// exchange.cu
+int launch_push_slabs(const double* local, double* const* peer_base, size_t slab_doubles, int nxi, int world, int rank,
+                      int k_first, cudaStream_t st);
+
 // gk.cu
 int launch_gk(int which, int nx, int nxi, int nt, const double* x, const double* xi, const double* t, double* out,
               cudaStream_t st);
