@@ -1001,7 +1001,7 @@ static int launch_pipe_one(int c, int n, int nxi, const double* xi_dev, int grid
         cudaMemcpyFromSymbol(h, g_k2stats, sizeof h);
         fprintf(stderr, "K2 pipe phases KID %d: node pass %.0f, evaluation %.0f, K(x,y)-K(y,x) %.0f cyc per group-round; tasks per group-round %.1f\n",
                 KID, h[6] ? (double)h[16] / h[6] : 0., h[6] ? (double)h[17] / h[6] : 0., h[6] ? (double)h[18] / h[6] : 0., h[6] ? (double)h[19] / h[6] : 0.);
-        fprintf(stderr, "K2 pipe stats KID %d: bookkeeper per round: wait-values %.0f, bookkeeping %.0f, wait-REQ %.0f cyc (%llu rounds) | evaluators per round: wait-requests %.0f, work %.0f cyc (%llu rounds) | block lifetime %.3g cyc, of which draining after the queue ran dry %.3g (%.1f %%)\n",
+        fprintf(stderr, "K2 pipe stats KID %d: bookkeeper per round: wait-values %.0f, bookkeeping to the hand-over %.0f, deferred extrapolation %.0f cyc (%llu rounds) | evaluators per round: wait-requests %.0f, work %.0f cyc (%llu rounds) | block lifetime %.3g cyc, of which draining after the queue ran dry %.3g (%.1f %%)\n",
                 KID, h[3] ? (double)h[0] / h[3] : 0., h[3] ? (double)h[1] / h[3] : 0., h[3] ? (double)h[2] / h[3] : 0., h[3],
                 h[6] ? (double)h[4] / h[6] : 0., h[6] ? (double)h[5] / h[6] : 0., h[6], (double)h[7], (double)h[15],
                 h[7] ? 100.0 * (double)h[15] / (double)h[7] : 0.0);

@@ -116,14 +116,17 @@ assemble_cst_pipe_kernel(int c, int n, int nxi, const double* __restrict__ xi_ar
             QSlot& S = sh.slot[myslot];
             QLists* myL = lists + (size_t)blockIdx.x * (2 * QG) + myslot;
             const int nint0 = mine ? S.nint : 0;
+            const bool term = mine && nint0 == 2 && S.term != 0;      // ended by the deferred extrapolation: these values are dropped
             double r_ = 0, e_ = 0, ra_ = 0, rc_ = 0;
-            if (nint0 == 2) qk21_reduce(sh.fv[myslot] + 21 * part, part ? S.a2 : S.a1, part ? S.b2 : S.b1, r_, e_, ra_, rc_);
+            if (nint0 == 2 && !term) qk21_reduce(sh.fv[myslot] + 21 * part, part ? S.a2 : S.a1, part ? S.b2 : S.b1, r_, e_, ra_, rc_);
             const double area2 = __shfl_down_sync(0xffffffffu, r_, 1);
             const double error2 = __shfl_down_sync(0xffffffffu, e_, 1);
             const double defab2 = __shfl_down_sync(0xffffffffu, rc_, 1);
             if (mine && part == 0) {
                 int state = QS_DONE;
-                if (nint0 == 1) {
+                if (term) {
+                    S.term = 0;
+                } else if (nint0 == 1) {
                     state = qags_first(S, sh.head[myslot], *myL, sh.fv[myslot]);
                     if (state == QS_CONTINUE) {
                         S.a1 = S.a;
@@ -134,7 +137,7 @@ assemble_cst_pipe_kernel(int c, int n, int nxi, const double* __restrict__ xi_ar
                         S.nint = 2;
                     }
                 } else if (nint0 == 2) {
-                    state = qags_step(S, sh.head[myslot], *myL, r_, e_, rc_, area2, error2, defab2);
+                    state = qags_step<true>(S, sh.head[myslot], *myL, r_, e_, rc_, area2, error2, defab2);
                 }
                 if (state == QS_DONE) {
                     if (nint0 != 0) {
@@ -168,6 +171,7 @@ assemble_cst_pipe_kernel(int c, int n, int nxi, const double* __restrict__ xi_ar
                             S.xx1 = rowtab[PRE_U1];
                             S.xx2 = rowtab[PRE_U2];
                             S.a1 = a; S.b1 = b; S.a2 = a; S.b2 = b;
+                            S.defer = 0; S.term = 0;
                             S.nint = 1;
                         }
                     }
@@ -184,17 +188,25 @@ assemble_cst_pipe_kernel(int c, int n, int nxi, const double* __restrict__ xi_ar
                 sh.act[g][bw] = (act != 0u) ? 1 : 0;
             }
             __syncwarp();
-            // the group's bookkeepers and the evaluators meet here; all of them then read the same act[] flags
-            // (rewritten only after the next VAL barrier, which needs every reader's arrival)
+            // hand-over: the bookkeepers only ARRIVE at the requests barrier (the evaluators wait on it), then run the
+            // extrapolation steps they deferred while the evaluators work on the requests
 #ifdef TKB_K2_STATS
             long long tb2_ = clock64();
 #endif
-            qp_bar_sync(QP_BAR_REQ0 + g, NRQ);
+            qp_bar_arrive(QP_BAR_REQ0 + g, NRQ);
+            if (mine && part == 0 && S.nint == 2 && S.defer != 0) {
+                S.defer = 0;
+                qags_deferred(S, sh.head[myslot], *myL);
+            }
+            __syncwarp();
+            if (BWG > 1) {                                           // the group's bookkeeping warps: act[] of the siblings is written
+                if (g == 0) qp_bar_sync_i<6>(32 * BWG); else qp_bar_sync_i<7>(32 * BWG);
+            }
 #ifdef TKB_K2_STATS
             if (lane == 0 && bw == 0) {
                 atomicAdd(&g_k2stats[0], (unsigned long long)(tb1_ - tb0_));          // bookkeeper waits for values
-                atomicAdd(&g_k2stats[1], (unsigned long long)(tb2_ - tb1_));          // bookkeeping
-                atomicAdd(&g_k2stats[2], (unsigned long long)(clock64() - tb2_));     // waits for the evaluators at REQ
+                atomicAdd(&g_k2stats[1], (unsigned long long)(tb2_ - tb1_));          // bookkeeping up to the hand-over
+                atomicAdd(&g_k2stats[2], (unsigned long long)(clock64() - tb2_));     // deferred extrapolation after the hand-over
                 atomicAdd(&g_k2stats[3], 1ULL);
             }
 #endif

@@ -23,6 +23,9 @@ struct QSlot {                       // scalar QUADPACK state of one instance (i
     int extrap, noext;
     int nanl;                        // an error estimate was a NaN: the ordered list may be unsorted (see qsort_bs_)
     int nint;                        // 0 idle, 1 first qk21 pending, 2 bisection pending
+    int defer;                       // qags_step<true> posted the next request before the extrapolation: qags_deferred is due
+    int term;                        // the deferred extrapolation ended the integration: result / last / ifail are final
+    double erlarg_pre;               // erlarg as the extrapolation step sees it (the posted state already carries errsum)
 };
 
 struct QLists {                      // per-slot interval lists in global memory (1-based)
@@ -56,6 +59,8 @@ static __device__ __noinline__ int qags_first(QSlot& S, QHead& H, QLists& L, con
     const double errbnd = fmax2(epsabs, epsrel * dres);
     S.last = 1;
     S.nanl = 0;
+    S.defer = 0;
+    S.term = 0;
     rlist[1] = result;
     elist[1] = abserr;
     iord[1] = 1;
@@ -114,6 +119,13 @@ L130:
 
 // one pass of the `do last = 2, limit` body after its two qk21 calls (integration.f90:455-577).
 // (area1, error1, defab1), (area2, error2, defab2) are the qk21 results of the request (a1,b1), (a2,b2).
+// DEFER: the epsilon-algorithm step (qextr, integration.f90:540-541: the longest piece of the bookkeeping chain, ~9 k
+// cycles) is taken off the path to the next request.  Everything QUADPACK does after it -- restart from the interval
+// with the largest error, halve `small`, erlarg = errsum -- does not depend on its numbers unless it ENDS the
+// integration, so that state is set and the request posted first; qags_deferred then runs the extrapolation and its
+// tests while the evaluators work on the request, and if it ends the integration the values of that one request are
+// dropped (S.term).  Same operations on the same numbers in QUADPACK's order per instance: result, last, ifail unchanged.
+template <bool DEFER = false>
 static __device__ __noinline__ int qags_step(QSlot& S, QHead& H, QLists& L, double area1, double error1, double defab1,
                                              double area2, double error2, double defab2)
 {
@@ -198,6 +210,17 @@ L40:
     }
     numrl2 = numrl2 + 1;
     rlist2[numrl2] = area;
+    if (DEFER) {
+        S.defer = 1;
+        S.erlarg_pre = erlarg;
+        maxerr = iord[1];
+        errmax = elist[maxerr];
+        nrmax = 1;
+        extrap = false;
+        small = small * 5.0e-01;
+        erlarg = errsum;
+        goto Lend;
+    }
 #ifdef TKB_K2_STATS
     tq0_ = clock64();
 #endif
@@ -251,6 +274,45 @@ Lend:
     S.b2 = blist[maxerr];
     S.erlast = errmax;
     return QS_CONTINUE;
+}
+
+// the extrapolation step that qags_step<true> left behind (integration.f90:540-556), run after the next request is posted
+static __device__ __noinline__ void qags_deferred(QSlot& S, QHead& H, QLists& L)
+{
+    const double epsabs = 1.0e-12, epsrel = 1.0e-06;
+    int numrl2 = S.numrl2, nres = S.nres, ktmin = S.ktmin, ifail = S.ifail;
+    double abserr = S.abserr, result = S.result, correc = S.correc, ertest = S.ertest;
+    const double errsum = S.errsum;
+    double reseps, abseps;
+    int status = 0;
+#ifdef TKB_K2_STATS
+    const long long tq0_ = clock64();
+#endif
+    qextr_(numrl2, H.rlist2, reseps, abseps, S.res3la, nres);
+#ifdef TKB_K2_STATS
+    atomicAdd(&g_k2stats[10], (unsigned long long)(clock64() - tq0_)); atomicAdd(&g_k2stats[11], 1ULL);
+#endif
+    ktmin = ktmin + 1;
+    if (ktmin > 5 && abserr < 1.0e-03 * errsum) ifail = 5;
+    if (abseps < abserr) {
+        ktmin = 0;
+        abserr = abseps;
+        result = reseps;
+        correc = S.erlarg_pre;
+        ertest = fmax2(epsabs, epsrel * fabs(reseps));
+        if (abserr <= ertest) status = 1;
+    }
+    if (status == 0) {
+        if (numrl2 == 1) S.noext = 1;
+        if (ifail == 5) status = 1;
+    }
+    S.numrl2 = numrl2; S.nres = nres; S.ktmin = ktmin; S.ifail = ifail;
+    S.abserr = abserr; S.result = result; S.correc = correc; S.ertest = ertest;
+    if (status != 0) {
+        S.last = S.last - 1;                 // the step that ran the extrapolation, not the request posted after it
+        qags_finish(S, H, L, status);
+        S.term = 1;
+    }
 }
 
 }  // namespace tkb
