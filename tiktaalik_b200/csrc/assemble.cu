@@ -88,6 +88,12 @@ __global__ void pre_table_kernel(int n, int nxi, const double* __restrict__ xi_a
     tab[e] = val;
 }
 
+#ifdef TKB_K2_STATS
+__device__ unsigned long long g_k2stats[24];      // in-kernel cycle counters of the stats build (K1 and K2)
+#define K1_CLK(slot) do { if (tid == 0) { const long long n_ = clock64(); atomicAdd(&g_k2stats[slot], (unsigned long long)(n_ - tc_)); tc_ = n_; } } while (0)
+#else
+#define K1_CLK(slot)
+#endif
 #ifndef TKB_K1_ROWS
 #define TKB_K1_ROWS 4
 #endif
@@ -116,7 +122,7 @@ struct K1Shared {
     unsigned short live[K1_ROWS * 2 * NNODE];
 };
 
-__global__ void __launch_bounds__(K1_THREADS, 1)
+__global__ void __launch_bounds__(K1_THREADS, (K1_ROWS <= 2) ? 2 : 1)
 assemble_fixed_kernel(int n, int nxi, const double* __restrict__ xi_arr, int grid_type,
                       double* __restrict__ P, double* __restrict__ diag)
 {
@@ -128,6 +134,9 @@ assemble_fixed_kernel(int n, int nxi, const double* __restrict__ xi_arr, int gri
     const int nrows = (n - i0 < K1_ROWS) ? (n - i0) : K1_ROWS;
     const double xi = xi_arr[ixi];
     const double* tab0 = d_pre_tab + ((size_t)ixi * n + (size_t)i0) * PRE_ROW;   // filled by pre_table_kernel
+#ifdef TKB_K2_STATS
+    long long tc_ = clock64();
+#endif
 
     // set-up, spread over a few threads of different warps (every piece is a chain of dependent log / pow / divisions):
     // integration.f90:27-35 breakpoints in eta space; Lagrange weights; eta of x_i; the row's one-argument logs/dilogs
@@ -177,6 +186,7 @@ assemble_fixed_kernel(int n, int nxi, const double* __restrict__ xi_arr, int gri
     }
     __syncthreads();
 
+    K1_CLK(0);
     // ---- phase 1a: one thread per (row, node, half): node, Jacobian / basis row, support class of the half ----
     // A half kernel whose support steps rho and theta_ERBL both vanish is an exact zero when every skipped piece
     // is finite (node_is_safe, as in K2); such halves -- about half of them -- are not evaluated, and the live
@@ -214,6 +224,7 @@ assemble_fixed_kernel(int n, int nxi, const double* __restrict__ xi_arr, int gri
         }
     }
     __syncthreads();
+    K1_CLK(1);
     // ---- phase 1b: the live halves, all 22 kernels each, in eight passes of two or three kernels ----
     // One evaluation of all 22 kernels is ~100 KB of straight-line code; as a single pass every warp streamed it from
     // L2 on its own (the warps drift apart by more than the instruction cache holds).  Here the transcendental values
@@ -236,6 +247,8 @@ assemble_fixed_kernel(int n, int nxi, const double* __restrict__ xi_arr, int gri
             const double* preO = sh.pre[r][half ^ 1];
             double tv[TV_N];
             if (active) node_values(X, Y, Xo, tv);
+            __syncthreads();
+            K1_CLK(2);
 #define TKB_K1_GROUP(MASK)                                                                   \
             __syncthreads();                                                                  \
             if (active) {                                                                     \
@@ -257,6 +270,7 @@ assemble_fixed_kernel(int n, int nxi, const double* __restrict__ xi_arr, int gri
         }
     }
     __syncthreads();
+    K1_CLK(3);
     // ---- phase 1c: K(x_i, y_k) from the two halves, in place ----
     for (int e = tid; e < nrows * NNODE; e += K1_THREADS) {
         const int r = e / NNODE, k = e - r * NNODE;
@@ -271,23 +285,38 @@ assemble_fixed_kernel(int n, int nxi, const double* __restrict__ xi_arr, int gri
     }
     __syncthreads();
 
+    K1_CLK(4);
     // ---- phase 2: one thread per (row, column j); replay qk21 per interval in the reference's order ----
     const size_t fstride = (size_t)nxi * n * n;
     // The six columns whose basis function is non-zero at x_i carry the subtraction term f_j(x_i) of the plus
     // kernels at every node (66 accumulation steps instead of the ~4 of an ordinary column).  They are split
-    // by kernel, one thread per (row, column, kernel), so that no thread walks all nodes for all 22 kernels.
-    for (int e = tid; e < nrows * 6 * NKERN; e += K1_THREADS) {
-        const int r = e / (6 * NKERN), t = e - r * 6 * NKERN;
+    // by kernel: one thread per (row, column, kernel pair), the pairs made of a plus-type and a regular kernel where
+    // possible so that every thread carries about the same work, and its two accumulation chains are independent.
+    // These 66-step items and the ordinary columns form ONE work list (heavy items first): as separate loops the
+    // 528 + 640 items of a block took four passes of 512 threads, two of them nearly empty, and the column replay
+    // was 58 % of the kernel.
+    constexpr int NPAIR = NKERN / 2;
+    const int nspec = nrows * 6 * NPAIR;
+    for (int e = tid; e < nspec + nrows * n; e += K1_THREADS) {
+    if (e < nspec) {
+        const int r = e / (6 * NPAIR), t = e - r * 6 * NPAIR;
         if (sh.allfinite[r] == 0) continue;            // a NaN/Inf kernel value poisons every column (0*NaN): dense pass below
-        const int jh = t / NKERN, f = t - NKERN * jh;
+        const int jh = t / NPAIR, pr = t - NPAIR * jh;
+        // the nine plus-type kernels 0, 5, 7, 8, 9, 18, 19, 20, 21 each with a regular one, then two regular pairs
+        constexpr int PA[NPAIR] = { K_K0QQ, K_A0GG, K_NSP, K_NSM, K_NSN, K_V1GG, K_A1GG, K_V1GGN, K_A1GGN, K_V1GQ, K_V1GQN };
+        constexpr int PB[NPAIR] = { K_A0QG, K_VMA0QG, K_A0GQ, K_VMA0GQ, K_VMA0GG, K_V1QQ, K_A1QQ, K_V1QG, K_A1QG, K_A1GQ, K_A1GQN };
+        int fa = PA[0], fb = PB[0];
+#pragma unroll
+        for (int q = 1; q < NPAIR; q++)
+            if (q == pr) { fa = PA[q]; fb = PB[q]; }
         const int j = sh.iSx[r] + jh;
         const double fx = sh.bx[r][jh];
         if (fx == 0.0) continue;
         const double (*sK)[NNODE] = sh.H[r][0];
-        const bool plus = is_plus(f);
-        double integral = 0.0;
+        const bool plusa = is_plus(fa), plusb = is_plus(fb);
+        double inta = 0.0, intb = 0.0;
         for (int iv = 0; iv < 6; iv++) {
-            double resk = 0.0;
+            double reska = 0.0, reskb = 0.0;
             for (int s = 0; s <= 10; s++) {
                 const int tt = (s == 0) ? 11 : ((s <= 5) ? 2 * s : 2 * (s - 5) - 1);
                 const int k1 = 21 * iv + ((s == 0) ? 0 : 2 * tt - 1);
@@ -297,28 +326,40 @@ assemble_fixed_kernel(int n, int nxi, const double* __restrict__ xi_arr, int gri
                 bool in2 = false;
                 int m2 = 0;
                 if (s != 0) { m2 = j - sh.iS[r][k2]; in2 = (m2 >= 0 && m2 < 6); }
-                if (!(plus || in1 || in2)) continue;
+                const bool doa = plusa || in1 || in2, dob = plusb || in1 || in2;
+                if (!(doa || dob)) continue;
                 const double fy1 = in1 ? sh.b[r][k1][m1] : 0.0;
                 const double J1 = sh.J[r][k1];
                 const double w = c_wgk[tt];
                 if (s == 0) {
-                    const double fc = plus ? (sK[f][k1] * (fy1 - fx)) * J1 : (sK[f][k1] * fy1) * J1;
-                    resk = w * fc;
+                    if (doa) { const double fc = plusa ? (sK[fa][k1] * (fy1 - fx)) * J1 : (sK[fa][k1] * fy1) * J1; reska = w * fc; }
+                    if (dob) { const double fc = plusb ? (sK[fb][k1] * (fy1 - fx)) * J1 : (sK[fb][k1] * fy1) * J1; reskb = w * fc; }
                 } else {
                     const double fy2 = in2 ? sh.b[r][k2][m2] : 0.0;
                     const double J2 = sh.J[r][k2];
-                    const double v1 = plus ? (sK[f][k1] * (fy1 - fx)) * J1 : (sK[f][k1] * fy1) * J1;
-                    const double v2 = plus ? (sK[f][k2] * (fy2 - fx)) * J2 : (sK[f][k2] * fy2) * J2;
-                    const double fsum = v1 + v2;
-                    resk = resk + w * fsum;
+                    if (doa) {
+                        const double v1 = plusa ? (sK[fa][k1] * (fy1 - fx)) * J1 : (sK[fa][k1] * fy1) * J1;
+                        const double v2 = plusa ? (sK[fa][k2] * (fy2 - fx)) * J2 : (sK[fa][k2] * fy2) * J2;
+                        const double fsum = v1 + v2;
+                        reska = reska + w * fsum;
+                    }
+                    if (dob) {
+                        const double v1 = plusb ? (sK[fb][k1] * (fy1 - fx)) * J1 : (sK[fb][k1] * fy1) * J1;
+                        const double v2 = plusb ? (sK[fb][k2] * (fy2 - fx)) * J2 : (sK[fb][k2] * fy2) * J2;
+                        const double fsum = v1 + v2;
+                        reskb = reskb + w * fsum;
+                    }
                 }
             }
-            integral = integral + resk * sh.hl[r][iv];
+            inta = inta + reska * sh.hl[r][iv];
+            intb = intb + reskb * sh.hl[r][iv];
         }
-        P[(size_t)f * fstride + ((size_t)ixi * n + (size_t)(i0 + r)) * n + (size_t)(j - 1)] = integral;
-    }
-    for (int e = tid; e < nrows * n; e += K1_THREADS) {
-        const int r = e / n, j = e - r * n + 1;
+        const size_t base = ((size_t)ixi * n + (size_t)(i0 + r)) * n + (size_t)(j - 1);
+        P[(size_t)fa * fstride + base] = inta;
+        P[(size_t)fb * fstride + base] = intb;
+    } else {
+        const int e2 = e - nspec;
+        const int r = e2 / n, j = e2 - r * n + 1;
         const bool dense = (sh.allfinite[r] == 0);
         const int iSx = sh.iSx[r];
         const int mx = j - iSx;
@@ -372,7 +413,10 @@ assemble_fixed_kernel(int n, int nxi, const double* __restrict__ xi_arr, int gri
 #pragma unroll
         for (int f = 0; f < NKERN; f++) P[(size_t)f * fstride + rowbase + (size_t)(j - 1)] = integral[f];
     }
+    }
 
+    __syncthreads();
+    K1_CLK(5);
     // ---- diagonal bookkeeping: f_i(x_i) and the analytic LO constants ----
     if ((tid & 127) == 0 && (tid >> 7) < nrows) {
         const int r = tid >> 7, i = i0 + r + 1;
@@ -403,7 +447,6 @@ assemble_fixed_kernel(int n, int nxi, const double* __restrict__ xi_arr, int gri
 constexpr int QLIMIT = 500;
 
 #ifdef TKB_K2_STATS
-__device__ unsigned long long g_k2stats[24];
 #endif
 
 template <typename T, int CAP>
@@ -943,6 +986,18 @@ int launch_assemble_fixed(int n, int nxi, const double* xi_dev, int grid_type, d
     if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
     assemble_fixed_kernel<<<grid, K1_THREADS, smem, st>>>(n, nxi, xi_dev, grid_type, P, diag);
     TKB_LAUNCH_CHECK();
+#ifdef TKB_K2_STATS
+    {
+        cudaStreamSynchronize(st);
+        unsigned long long h[24];
+        cudaMemcpyFromSymbol(h, g_k2stats, sizeof h);
+        const double nb = (double)grid.x * grid.y;
+        fprintf(stderr, "K1 phases, cycles per block (%d rows): set-up %.0f, nodes + classes %.0f, node transcendentals %.0f, 22 kernels in 8 passes %.0f, combine halves %.0f, column replay %.0f\n",
+                K1_ROWS, h[0] / nb, h[1] / nb, h[2] / nb, h[3] / nb, h[4] / nb, h[5] / nb);
+        unsigned long long z[24] = { 0 };
+        cudaMemcpyToSymbol(g_k2stats, z, sizeof z);
+    }
+#endif
     return 0;
 }
 
