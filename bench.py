@@ -58,7 +58,9 @@ WORKLOADS = {
                    "Q2 4->10 GeV^2, 4 chunks of 128 xi per rank"},
 }
 FAMILIES = [(0, 1), (0, -1), (1, 1), (3, 1)]            # (type, nstype): VNS+, VNS-, VSG, ASG   (TKB_VNS = 0, VSG = 1, ASG = 3)
-CPU_KIND_NOTE = "restated C port of the Fortran (oracle/, -O3 -ffp-contract=off, own log/pow from IEEE operations), OpenMP over x rows"
+CPU_KIND_NOTE = ("restated C port of the Fortran built like the reference itself (oracle/libtko_fast.so: -Ofast -march=x86-64-v3 "
+                 "-fopenmp, libm log/pow; f90src/CMakeLists.txt:12-14), OpenMP over x rows; timing only -- the bit-exact checker "
+                 "build (own log/pow, -O3 -ffp-contract=off) is about 1.9x slower")
 
 
 def global_xi(wl, world):
@@ -133,9 +135,11 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_reference_step(nx, xi_sample, threads):
-    """One pass of the reference-shaped CPU algorithm (oracle mode 0) over xi_sample; returns seconds."""
+def cpu_reference_step(nx, xi_sample, threads, fast=True):
+    """One pass of the reference-shaped CPU algorithm (oracle mode 0) over xi_sample; returns seconds.
+    fast: the timing-only build with the reference's own compiler flags and libm (oracle/tko_fp.h, TKO_LIBM)."""
     from oracle import tko
+    tko.use_fast_build(fast)
     os.environ["OMP_NUM_THREADS"] = str(threads)
     t0 = time.perf_counter()
     tko.initialize_kernels(nx, xi_sample, GRID_TYPE, mode=0)
@@ -536,8 +540,9 @@ def main():
             xi_all = global_xi(wl, world)
             sample = cpu_sample(xi_all)
             t = cpu_reference_step(NX, sample, threads)
+            t_exact = cpu_reference_step(NX, sample, threads, fast=False)
             line["cpu_baseline"] = {"value": sample.shape[0] / t, "unit": "xi pts/s", "cores": threads, "kind": "port",
-                                    "kind_note": CPU_KIND_NOTE,
+                                    "kind_note": CPU_KIND_NOTE, "bit_exact_checker_build_value": sample.shape[0] / t_exact,
                                     "sample": "8 of %d xi (strided over the whole list, %.2e .. %.2e, both ends included), full nx=%d NLO "
                                               "assembly + RK4, reference-shaped unfactored loop nest, %.1f s"
                                               % (len(xi_all), sample[0], sample[-1], NX, t)}

@@ -14,6 +14,16 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
+_FAST = False
+
+
+def use_fast_build(on=True):
+    """bench.py's CPU legs only: switch to libtko_fast.so (libm log / pow, -Ofast -march=native: the reference's own
+    build flags) for TIMING.  Never used as a checker: its numbers differ from the oracle's in the last bits."""
+    global _LIB, _FAST
+    if bool(on) != _FAST:
+        _FAST = bool(on)
+        _LIB = None
 
 KERNEL_NAMES = [
     "K0_qq_pls", "KA0_qG_reg", "KVmA0_qG_reg", "KA0_Gq_reg", "KVmA0_Gq_reg", "KA0_GG_pls", "KVmA0_GG_reg",
@@ -30,7 +40,7 @@ _ip = C.POINTER(C.c_int)
 
 def build(force=False):
     """Compile libtko.so with the committed Makefile (gcc only)."""
-    so = os.path.join(_HERE, "libtko.so")
+    so = os.path.join(_HERE, "libtko_fast.so" if _FAST else "libtko.so")
     srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".c", ".h")) or f == "Makefile"]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-s", "-C", _HERE], stdout=subprocess.DEVNULL)

@@ -197,4 +197,15 @@ static inline double tko_pow15_capped(double t)
     return tko_pow(t, 1.5);
 }
 
-#endif /* TKO_FP_H */
+/* TIMING-ONLY build (libtko_fast.so, bench.py's CPU legs): libm's log / pow and the reference's own compiler flags
+ * (f90src/CMakeLists.txt:12-14: -Ofast -march=native -fopenmp; here -march=x86-64-v3, AVX2 + FMA, because the built
+ * library travels to another host), i.e. what a real build of the Fortran spends per
+ * evaluation rather than what the bit-exact restatement above spends.  Its numbers differ from the oracle's in the
+ * last bits (and QUADPACK may take a few more or fewer bisections); it is never used as a checker. */
+#ifdef TKO_LIBM
+#define tko_log(x) log(x)
+#define tko_pow(x, y) pow((x), (y))
+#define tko_pow15_capped(t) (((t) >= 1.0) ? 1.0 : pow((t), 1.5))
+#endif
+
+#endif
