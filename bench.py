@@ -185,6 +185,9 @@ def main():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1: the exchange by copy-engine pushes into peer memory (default) or by NCCL all-gathers")
+    ap.add_argument("--verify", action="store_true",
+                    help="N > 1: after the timed region check the gathered arrays (own slabs bit for bit, foreign slabs by the "
+                         "owners' checksums) for the last chunk of the last step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the e2e, application and CPU legs (profiling runs)")
     args = ap.parse_args()
@@ -347,6 +350,30 @@ def main():
                      "ms_per_step_overlapped_with_assembly": g_ms, "bytes_received_per_rank_per_step": int(recv_bytes),
                      "alone_ms_per_chunk": float(t_al.item()), "alone_GBps_per_rank": chunk_recv / (float(t_al.item()) * 1e-3) / 1e9,
                      "chunks_per_step": nchunk, "inside_timed_region": True}
+
+    verify = None
+    if world > 1 and args.verify:
+        # the last chunk's matrices are still in the library: every rank's slabs must sit at (k_first + k) * world + rank
+        # of every rank's gathered array
+        barrier()
+        ok = True
+        k_first = (nchunk - 1) * per_chunk
+        f90 = tk.f90wrap.matrices.dummy
+        f90.zero_copy = True
+        local = [tk.matrices.matrix_VNS(1), tk.matrices.matrix_VNS(-1), tk.matrices.matrix_VSG(), tk.matrices.matrix_ASG()]
+        f90.zero_copy = False
+        for loc, out in zip(local, gathered):
+            store = out.permute(2, 3, 0, 1) if use_p2p else out                  # [xi][Q2][m][m]
+            blk = store[k_first * world:(k_first + per_chunk) * world].reshape(per_chunk, world, *store.shape[1:])
+            ok = ok and torch.equal(blk[:, rank], loc.permute(2, 3, 0, 1))
+            mine = loc.nan_to_num().sum().reshape(1)
+            owners = [torch.zeros_like(mine) for _ in range(world)]
+            dist.all_gather(owners, mine)
+            for r in range(world):
+                ok = ok and bool(torch.equal(blk[:, r].nan_to_num().sum().reshape(1), owners[r]))
+        flag = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        verify = "OK" if int(flag.item()) == 1 else "MISMATCH"
 
     # algorithmic work of K2 on this rank: integrand evaluations of the executed QUADPACK path (of the last chunk,
     # scaled to the step: the chunks are strided samples of the same list)
@@ -530,6 +557,8 @@ def main():
             line["e2e"] = {"value": None, "unit": "xi pts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                            "note": "not measured in this mode"}
         if allgather is not None:
+            if verify is not None:
+                allgather["verified_last_chunk"] = verify
             line["allgather"] = allgather
         if application is not None:
             line["application"] = application
