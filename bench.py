@@ -141,6 +141,10 @@ def cpu_reference_step(nx, xi_sample, threads, fast=True):
     from oracle import tko
     tko.use_fast_build(fast)
     os.environ["OMP_NUM_THREADS"] = str(threads)
+    try:        # torchrun exports OMP_NUM_THREADS=1 and libgomp has read it by now: set the thread count directly
+        C.CDLL("libgomp.so.1").omp_set_num_threads(int(threads))
+    except OSError:
+        pass
     t0 = time.perf_counter()
     tko.initialize_kernels(nx, xi_sample, GRID_TYPE, mode=0)
     tko.initialize_evolution_matrices(Q2, nlo=True)
