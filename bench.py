@@ -238,8 +238,10 @@ def main():
     if world > 1:
         gather_stream = torch.cuda.Stream(device=dev)
         if use_p2p:
-            gathered = tk.shard.init_p2p(NX, xi.shape[0] * world, Q2.shape[0])
-        else:
+            gathered = tk.shard.init_p2p(NX, xi.shape[0] * world, Q2.shape[0], strict=False)
+            if gathered is None:                 # CUDA IPC between the ranks is not available on this box: NCCL instead
+                use_p2p = False
+        if not use_p2p:
             tk.shard.init_capi()
             gathered = [torch.empty((xi.shape[0] * world, Q2.shape[0], NX * (1 if t == 0 else 2), NX * (1 if t == 0 else 2)),
                                     dtype=torch.float64, device=dev) for t, _ in FAMILIES]
@@ -350,7 +352,8 @@ def main():
         allgather = {"collective": ("copy-engine pushes into every rank's receive buffer over NVLink (tkb_p2p_push_matrices: one strided "
                                     "cudaMemcpy2DAsync per peer and matrix family, CUDA IPC peer memory, no SMs)" if use_p2p else
                                     "ncclAllGather per xi, one NCCL group per matrix family (tkb_allgather_matrices_strided)")
-                                   + "; 4 families, result in the order of the global xi list",
+                                   + "; 4 families, result in the order of the global xi list"
+                                   + ("" if use_p2p or args.gather == "nccl" else " (fallback: CUDA IPC peer mapping failed on this box)"),
                      "ms_per_step_overlapped_with_assembly": g_ms, "bytes_received_per_rank_per_step": int(recv_bytes),
                      "alone_ms_per_chunk": float(t_al.item()), "alone_GBps_per_rank": chunk_recv / (float(t_al.item()) * 1e-3) / 1e9,
                      "chunks_per_step": nchunk, "inside_timed_region": True}

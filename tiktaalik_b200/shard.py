@@ -167,29 +167,50 @@ _P2P_SLOTS = {"matrix_VNS+": 0, "matrix_VNS-": 1, "matrix_VSG": 2, "matrix_ASG":
 _P2P_FAMILY = {0: (0, 1), 1: (0, -1), 2: (1, 1), 3: (3, 1)}        # slot -> (tkb type, nstype)
 
 
-def init_p2p(nx, nxi_total, nq2, group=None):
+def init_p2p(nx, nxi_total, nq2, group=None, strict=True):
     """Allocate this rank's four receive buffers (VNS+, VNS-, VSG, ASG; [xi_total][Q2][m][m]) and map every peer's.
-    Returns the four buffers as tensors of logical shape (m, m, nxi_total, nQ2)."""
+    Returns the four buffers as tensors of logical shape (m, m, nxi_total, nQ2).  Every step is agreed on by all ranks
+    (a failure on one rank -- e.g. CUDA IPC not permitted between the processes -- is a failure on all, so nobody is left
+    waiting in a collective); strict=False returns None instead of raising, for callers with another exchange to fall
+    back to."""
     import ctypes as C
     import torch.distributed as dist
     from . import _lib
     L = _lib.lib()
-    _lib.require_cuda()
+    dev = _lib.require_cuda()
     rank, world = dist.get_rank(group), dist.get_world_size(group)
-    views, handles = [], []
-    for slot in range(4):
-        m = nx * (2 if slot >= 2 else 1)
-        addr = C.c_void_p()
-        _lib.check(L.tkb_p2p_alloc(slot, int(nxi_total) * int(nq2) * m * m * 8, C.byref(addr)))
-        views.append(_lib.view_tensor(addr.value, (nxi_total, nq2, m, m)).permute(2, 3, 0, 1))
-        buf = C.create_string_buffer(64)
-        _lib.check(L.tkb_p2p_handle(slot, buf))
-        handles.append(buf.raw)
-    gathered = [None] * world
-    dist.all_gather_object(gathered, handles, group=group)
-    for slot in range(4):
-        _lib.check(L.tkb_p2p_open(slot, rank, world, b"".join(gathered[r][slot] for r in range(world))))
-    return views
+
+    def agreed(ok):
+        flag = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        return int(flag.item()) == 1
+
+    views, handles, err = [], [], None
+    try:
+        for slot in range(4):
+            m = nx * (2 if slot >= 2 else 1)
+            addr = C.c_void_p()
+            _lib.check(L.tkb_p2p_alloc(slot, int(nxi_total) * int(nq2) * m * m * 8, C.byref(addr)))
+            views.append(_lib.view_tensor(addr.value, (nxi_total, nq2, m, m)).permute(2, 3, 0, 1))
+            buf = C.create_string_buffer(64)
+            _lib.check(L.tkb_p2p_handle(slot, buf))
+            handles.append(buf.raw)
+    except RuntimeError as exc:
+        err = exc
+    if agreed(err is None):
+        gathered = [None] * world
+        dist.all_gather_object(gathered, handles, group=group)
+        try:
+            for slot in range(4):
+                _lib.check(L.tkb_p2p_open(slot, rank, world, b"".join(gathered[r][slot] for r in range(world))))
+        except RuntimeError as exc:
+            err = exc
+        if agreed(err is None):
+            return views
+    L.tkb_p2p_close()
+    if strict:
+        raise RuntimeError("tiktaalik_b200.shard.init_p2p failed on at least one rank" + (": %s" % err if err else ""))
+    return None
 
 
 def push_matrices_p2p(k_first=0, stream=None):
