@@ -81,6 +81,8 @@ def evolver_through_the_bottom_threshold():
     lo = Darwin.evolveGPDs(grid)
     nlo = Darwin.evolveGPDs(grid, nlo=True)
     Sigma0 = u0 + d0 + s0 - np.flip(u0 + d0 + s0, axis=0)
+    # (with evolution.REFERENCE_BUGS, the default, V-type NLO re-applies the previous segment's matrix in the last segment
+    # exactly as the reference does, evolution.py:273-280, so this Q2 axis is longer than nQ2)
     Sigma_evo, g_evo = Darwin.evolveSinglet(Sigma0, g0, nlo=True)
     umin_evo = Darwin.evolveNS(u0 + np.flip(u0, axis=0), nlo=True, ns_type=-1)
     return {"gpd_grid_ini": tuple(grid.shape), "gpd_evo_lo": tuple(lo.shape), "gpd_evo_nlo": tuple(nlo.shape),
