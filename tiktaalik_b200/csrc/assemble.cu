@@ -718,6 +718,7 @@ static __device__ __noinline__ void qk21_reduce(const double* fv, double a, doub
 }  // namespace tkb
 #include "qags_step.cuh"
 #include "assemble_cst_pipe.cuh"
+#include "assemble_cst_pair.cuh"
 #include "assemble_cst_queue.cuh"
 namespace tkb {
 
@@ -1067,6 +1068,38 @@ static int launch_pipe_one(int c, int n, int nxi, const double* xi_dev, int grid
     return 0;
 }
 
+// KV1_NSp and KV1_NSm in one launch (assemble_cst_pair.cuh)
+template <int KA, int KB>
+static int launch_pair_one(int ca, int cb, int n, int nxi, const double* xi_dev, int grid_type, QLists* lists, int sms,
+                           unsigned long long* counter, double* cst_res, int* cst_last, int* cst_ifail, cudaStream_t st)
+{
+    constexpr int QP = 8, NT = 768;
+    const size_t smem = sizeof(QPairShared<QP>);
+    auto kern = assemble_cst_pair_kernel<KA, KB, QP, NT>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
+    const unsigned long long total = (unsigned long long)nxi * n * 3ULL;
+    long long nb = (long long)sms;
+    const long long want = (long long)((total + 2 * QP - 1) / (2 * QP));
+    if (nb > want) nb = want;
+    kern<<<(int)nb, NT, smem, st>>>(ca, cb, n, nxi, xi_dev, grid_type, lists, counter, cst_res, cst_last, cst_ifail);
+    TKB_LAUNCH_CHECK();
+#ifdef TKB_K2_STATS
+    {
+        cudaStreamSynchronize(st);
+        unsigned long long h[24];
+        cudaMemcpyFromSymbol(h, g_k2stats, sizeof h);
+        const double nw = h[6] ? (double)h[6] : 1., nr = h[5] ? (double)h[5] : 1., nb = h[3] ? (double)h[3] : 1.;
+        fprintf(stderr, "K2 pair KID %d+%d: evaluator warp per group-round (mean over warps): wait-requests %.0f, node pass %.0f, barrier %.0f, evaluation %.0f, barrier %.0f, K pass + hand-over %.0f cyc; tasks per group-round %.1f (%.0f group-rounds) | bookkeeper per round: wait-values %.0f, to hand-over %.0f, deferred %.0f cyc (%.0f rounds), active states %.1f of %d | pair slots per round: shared request %.2f, different requests %.2f, one state waiting %.2f\n",
+                KA, KB, h[4] / nw, h[16] / nw, h[7] / nw, h[17] / nw, h[15] / nw, h[18] / nw, h[19] / nr, nr,
+                h[0] / nb, h[1] / nb, h[2] / nb, nb, h[13] / nb, 2 * QP, h[14] / nr, h[21] / nr, h[22] / nr);
+        unsigned long long z[24] = { 0 };
+        cudaMemcpyToSymbol(g_k2stats, z, sizeof z);
+    }
+#endif
+    return 0;
+}
+
 template <int KID>
 static int launch_queue_one(int c, int n, int nxi, const double* xi_dev, int grid_type, QLists* lists, int sms,
                             unsigned long long* counter, double* cst_res, int* cst_last, int* cst_ifail, cudaStream_t st)
@@ -1131,11 +1164,18 @@ int launch_assemble_cst(int n, int nxi, const double* xi_dev, int grid_type, voi
                                       cst_last, cst_ifail, strm)                                                       \
               : launch_pipe_one<KID>(c, n, nxi, xi_dev, grid_type, Lp + region * (c), sms, counters + (c), cst_res,    \
                                      cst_last, cst_ifail, strm)) return 1;
-    // the expensive, long-tailed constants first
+    // the expensive, long-tailed constants first.  KV1_NSp and KV1_NSm share one launch (one evaluation gives both
+    // integrands; TKB_K2_PAIR=0 runs them separately for comparison)
+    static const bool pair_ns = [] { const char* e = getenv("TKB_K2_PAIR"); return !(e && e[0] == '0'); }();
     K2_ONE(3, K_V1GG, side[0])
-    K2_ONE(0, K_NSP, side[1])
+    if (pair_ns && !queue) {
+        if (launch_pair_one<K_NSP, K_NSM>(0, 1, n, nxi, xi_dev, grid_type, Lp + region * 0, sms, counters + 0, cst_res, cst_last,
+                                          cst_ifail, side[1])) return 1;
+    } else {
+        K2_ONE(0, K_NSP, side[1])
+    }
     K2_ONE(4, K_A1GG, side[2])
-    K2_ONE(1, K_NSM, side[5])
+    if (!(pair_ns && !queue)) { K2_ONE(1, K_NSM, side[5]) }
     K2_ONE(5, K_V1GGN, side[3])
     K2_ONE(6, K_A1GGN, side[4])
     K2_ONE(2, K_NSN, side[6])

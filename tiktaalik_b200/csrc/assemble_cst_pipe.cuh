@@ -68,6 +68,27 @@ __device__ __forceinline__ void qp_bar_sync(int id, int count)
     default: qp_bar_sync_i<5>(count); break;
     }
 }
+// threadIdx.x re-read behind an opaque asm: index arithmetic derived from it is redone in every phase of every round
+// (a few integer instructions) instead of being hoisted out of the round loop, where the evaluation's register pressure
+// spills it to local memory -- with ~200 KB of the SM given to shared memory those reloads miss L1 and serialise
+// (measured: 9.6 k of 25 k cycles per group-round in the K pass of the paired kernel)
+__device__ __forceinline__ int qp_tid()
+{
+#ifdef TKB_K2_PLAIN_TID
+    return (int)threadIdx.x;
+#else
+    int t;
+    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(t));
+    return t;
+#endif
+}
+// clock read that keeps its place among the barrier instructions (qp_clk() may be scheduled across an asm barrier)
+__device__ __forceinline__ long long qp_clk()
+{
+    long long t;
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) :: "memory");
+    return t;
+}
 __device__ __forceinline__ void qp_bar_arrive(int id, int count)
 {
     switch (id) {
@@ -106,11 +127,11 @@ assemble_cst_pipe_kernel(int c, int n, int nxi, const double* __restrict__ xi_ar
         bool exhausted = false;
         for (int round = 0;; round++) {
 #ifdef TKB_K2_STATS
-            long long tb0_ = clock64();
+            long long tb0_ = qp_clk();
 #endif
             if (round >= 1) qp_bar_sync(QP_BAR_VAL0 + g, NRQ);      // the first round only pulls instances
 #ifdef TKB_K2_STATS
-            long long tb1_ = clock64();
+            long long tb1_ = qp_clk();
 #endif
             const int myslot = g * QG + (mine ? (bw + BWG * (lane >> 1)) : 0);
             QSlot& S = sh.slot[myslot];
@@ -151,7 +172,7 @@ assemble_cst_pipe_kernel(int c, int n, int nxi, const double* __restrict__ xi_ar
                     if (!exhausted) {
                         const unsigned long long inst = atomicAdd(counter, 1ULL);
 #ifdef TKB_K2_STATS
-                        if (inst >= total && sh.t_exh == 0) sh.t_exh = clock64();
+                        if (inst >= total && sh.t_exh == 0) sh.t_exh = qp_clk();
 #endif
                         if (inst >= total) exhausted = true;
                         else {
@@ -191,7 +212,7 @@ assemble_cst_pipe_kernel(int c, int n, int nxi, const double* __restrict__ xi_ar
             // hand-over: the bookkeepers only ARRIVE at the requests barrier (the evaluators wait on it), then run the
             // extrapolation steps they deferred while the evaluators work on the requests
 #ifdef TKB_K2_STATS
-            long long tb2_ = clock64();
+            long long tb2_ = qp_clk();
 #endif
             qp_bar_arrive(QP_BAR_REQ0 + g, NRQ);
             if (mine && part == 0 && S.nint == 2 && S.defer != 0) {
@@ -206,7 +227,7 @@ assemble_cst_pipe_kernel(int c, int n, int nxi, const double* __restrict__ xi_ar
             if (lane == 0 && bw == 0) {
                 atomicAdd(&g_k2stats[0], (unsigned long long)(tb1_ - tb0_));          // bookkeeper waits for values
                 atomicAdd(&g_k2stats[1], (unsigned long long)(tb2_ - tb1_));          // bookkeeping up to the hand-over
-                atomicAdd(&g_k2stats[2], (unsigned long long)(clock64() - tb2_));     // deferred extrapolation after the hand-over
+                atomicAdd(&g_k2stats[2], (unsigned long long)(qp_clk() - tb2_));     // deferred extrapolation after the hand-over
                 atomicAdd(&g_k2stats[3], 1ULL);
             }
 #endif
@@ -221,17 +242,17 @@ assemble_cst_pipe_kernel(int c, int n, int nxi, const double* __restrict__ xi_ar
     // ======================= evaluators =======================
     const int etid = tid - NBK;
 #ifdef TKB_K2_STATS
-    const long long tk0_ = clock64();
+    const long long tk0_ = qp_clk();
 #endif
     int alive = 3;
     for (int g = 0; alive != 0; g ^= 1) {
         if (!((alive >> g) & 1)) continue;
 #ifdef TKB_K2_STATS
-        long long te0_ = clock64();
+        long long te0_ = qp_clk();
 #endif
         qp_bar_sync(QP_BAR_REQ0 + g, NRQ);
 #ifdef TKB_K2_STATS
-        long long te1_ = clock64();
+        long long te1_ = qp_clk();
 #endif
         {
             int any = 0;
@@ -243,6 +264,7 @@ assemble_cst_pipe_kernel(int c, int n, int nxi, const double* __restrict__ xi_ar
         // listed per direction so that a warp evaluates one direction (one set of pre-computed values) ----
         // (warp-aggregated compaction: one shared-memory atomic per warp and list instead of one per thread)
         for (int e0 = 0; e0 < QG * 42; e0 += NE) {
+            const int etid = qp_tid() - NBK;
             const int e = e0 + etid;
             const bool inr = e < QG * 42;
             const int s = g * QG + (inr ? e / 42 : 0), node = inr ? e % 42 : 0;
@@ -297,6 +319,7 @@ assemble_cst_pipe_kernel(int c, int n, int nxi, const double* __restrict__ xi_ar
         }
         // one-argument transcendental values of the instances that start in this round (nint == 1)
         if (qp_pre_need<KID>() != 0u) {
+            const int etid = qp_tid() - NBK;
             for (int e = etid; e < QG * 2 * PRE_N; e += NE) {
                 const int s = g * QG + e / (2 * PRE_N), v = e % (2 * PRE_N);
                 const QSlot& S = sh.slot[s];
@@ -306,7 +329,7 @@ assemble_cst_pipe_kernel(int c, int n, int nxi, const double* __restrict__ xi_ar
         }
         qp_bar_sync(QP_BAR_EV, NE);
 #ifdef TKB_K2_STATS
-        const long long tp1_ = clock64();
+        const long long tp1_ = qp_clk();
 #endif
 
         // ---- E: evaluate the live half kernels.  Four segments (direction x {full, erbl-only}), each padded
@@ -314,14 +337,23 @@ assemble_cst_pipe_kernel(int c, int n, int nxi, const double* __restrict__ xi_ar
         // expensive segment first (K(y,x) needs more transcendental values than K(x,y)), so that the cheap
         // chunks fill the end of the phase ----
         {
-            const int n0 = *(volatile int*)&sh.nfull[g][1], n1 = *(volatile int*)&sh.nfull[g][0];
-            const int n2 = HAS_ERBL ? *(volatile int*)&sh.nerbl[g][1] : 0, n3 = HAS_ERBL ? *(volatile int*)&sh.nerbl[g][0] : 0;
-            const int p0 = (n0 + 31) & ~31, p1 = p0 + ((n1 + 31) & ~31), p2 = p1 + ((n2 + 31) & ~31), p3 = p2 + ((n3 + 31) & ~31);
-            const int elane = etid & 31;
+            const int elane = qp_tid() & 31;
+#ifdef TKB_K2_HOIST_SEG
+                // the segment sizes are re-read per chunk (four shared-memory loads) rather than kept live across the evaluation
+                const int n0 = *(volatile int*)&sh.nfull[g][1], n1 = *(volatile int*)&sh.nfull[g][0];
+                const int n2 = HAS_ERBL ? *(volatile int*)&sh.nerbl[g][1] : 0, n3 = HAS_ERBL ? *(volatile int*)&sh.nerbl[g][0] : 0;
+                const int p0 = (n0 + 31) & ~31, p1 = p0 + ((n1 + 31) & ~31), p2 = p1 + ((n2 + 31) & ~31), p3 = p2 + ((n3 + 31) & ~31);
+#endif
             for (;;) {
                 int chunk = 0;
                 if (elane == 0) chunk = atomicAdd(&sh.next[g], 1);
                 chunk = __shfl_sync(0xffffffffu, chunk, 0);
+#ifndef TKB_K2_HOIST_SEG
+                // the segment sizes are re-read per chunk (four shared-memory loads) rather than kept live across the evaluation
+                const int n0 = *(volatile int*)&sh.nfull[g][1], n1 = *(volatile int*)&sh.nfull[g][0];
+                const int n2 = HAS_ERBL ? *(volatile int*)&sh.nerbl[g][1] : 0, n3 = HAS_ERBL ? *(volatile int*)&sh.nerbl[g][0] : 0;
+                const int p0 = (n0 + 31) & ~31, p1 = p0 + ((n1 + 31) & ~31), p2 = p1 + ((n2 + 31) & ~31), p3 = p2 + ((n3 + 31) & ~31);
+#endif
                 const int idx = chunk * 32 + elane;
                 if (chunk * 32 >= p3) break;
                 const int seg = (idx < p0) ? 0 : ((idx < p1) ? 1 : ((idx < p2) ? 2 : 3));
@@ -347,12 +379,12 @@ assemble_cst_pipe_kernel(int c, int n, int nxi, const double* __restrict__ xi_ar
         }
         qp_bar_sync(QP_BAR_EV, NE);
 #ifdef TKB_K2_STATS
-        const long long tp2_ = clock64();
+        const long long tp2_ = qp_clk();
         const int ntask_ = sh.nfull[g][0] + sh.nfull[g][1] + sh.nerbl[g][0] + sh.nerbl[g][1];
 #endif
 
         // ---- K: K(x,y,xi) - K(y,x,xi) per node ----
-        for (int e = etid; e < QG * 42; e += NE) {
+        for (int e = qp_tid() - NBK; e < QG * 42; e += NE) {
             const int s = g * QG + e / 42, node = e % 42;
             const QSlot& S = sh.slot[s];
             if (node < 21 * S.nint) {
@@ -366,18 +398,18 @@ assemble_cst_pipe_kernel(int c, int n, int nxi, const double* __restrict__ xi_ar
 #ifdef TKB_K2_STATS
         if (etid == 0) {
             atomicAdd(&g_k2stats[4], (unsigned long long)(te1_ - te0_));              // evaluators wait for requests
-            atomicAdd(&g_k2stats[5], (unsigned long long)(clock64() - te1_));         // N+C, E, K
+            atomicAdd(&g_k2stats[5], (unsigned long long)(qp_clk() - te1_));         // N+C, E, K
             atomicAdd(&g_k2stats[6], 1ULL);
             atomicAdd(&g_k2stats[16], (unsigned long long)(tp1_ - te1_));             // node pass
             atomicAdd(&g_k2stats[17], (unsigned long long)(tp2_ - tp1_));             // evaluation
-            atomicAdd(&g_k2stats[18], (unsigned long long)(clock64() - tp2_));        // K(x,y) - K(y,x)
+            atomicAdd(&g_k2stats[18], (unsigned long long)(qp_clk() - tp2_));        // K(x,y) - K(y,x)
             atomicAdd(&g_k2stats[19], (unsigned long long)ntask_);
         }
 #endif
     }
 #ifdef TKB_K2_STATS
     if (etid == 0) {
-        const long long now_ = clock64();
+        const long long now_ = qp_clk();
         atomicAdd(&g_k2stats[7], (unsigned long long)(now_ - tk0_));                              // block lifetime
         atomicAdd(&g_k2stats[15], (unsigned long long)(sh.t_exh ? now_ - sh.t_exh : 0));           // of which after the queue ran dry
     }
