@@ -1027,6 +1027,9 @@ int launch_assemble_fixed(int n, int nxi, const double* xi_dev, int grid_type, d
 #ifndef TKB_QPBPS
 #define TKB_QPBPS 1
 #endif
+#ifndef TKB_QPP
+#define TKB_QPP 8                 // pair kernel: pair slots per group
+#endif
 #ifndef TKB_QPBWG
 #define TKB_QPBWG 1
 #endif
@@ -1073,7 +1076,7 @@ template <int KA, int KB>
 static int launch_pair_one(int ca, int cb, int n, int nxi, const double* xi_dev, int grid_type, QLists* lists, int sms,
                            unsigned long long* counter, double* cst_res, int* cst_last, int* cst_ifail, cudaStream_t st)
 {
-    constexpr int QP = 8, NT = 768;
+    constexpr int QP = TKB_QPP, NT = 768;
     const size_t smem = sizeof(QPairShared<QP>);
     auto kern = assemble_cst_pair_kernel<KA, KB, QP, NT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
