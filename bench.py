@@ -540,7 +540,7 @@ def main():
                                     "assembly_K1_and_K2": stage[1], "K3K4_compose_rk4": stage[2]}},
             "clocks": clocks,
             "gpu_launches": int(launches),
-            "roofline": {"bound": "fp64", "kernel": "K2, the QAGS constants: assemble_cst_pipe_kernel<KID> x 7 launches; duration = the assembly span, which also contains the overlapped fixed-quadrature kernel K1",
+            "roofline": {"bound": "fp64", "kernel": "K2, the QAGS constants: six launches (assemble_cst_pair_kernel for KV1_NSp + KV1_NSm, assemble_cst_pipe_kernel<KID> for the other five); duration = the assembly span, which also contains the overlapped fixed-quadrature kernel K1",
                          "achieved": k2_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": k2_tflops / fp64_peak if fp64_peak else None, "traffic": fpe.get("traffic_bytes"),
                          "traffic_source": fpe.get("traffic_source"),

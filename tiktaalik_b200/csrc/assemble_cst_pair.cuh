@@ -20,7 +20,7 @@ struct QPairShared {
     QSlot slot[2 * QP * 2];               // [group][pair][state]: s = (g * QP + p) * 2 + st
     QHead head[2 * QP * 2];
     double ny[2 * QP][2][42][2];          // [pair slot][node set][node]: 0.5 (1 +- y/xi)
-    double hv[2 * QP][2][168][2];         // [pair slot][node set][task = 4 node + 2 dir + half][state]: half-kernel values
+    double hv[2 * QP][2][2][168];         // [pair slot][node set][state][42 (2 dir + half) + node]: half-kernel values (the K pass reads consecutive nodes)
     double fv[2 * QP * 2][42];            // [state][node]: integrand values handed to the bookkeepers
     double pre[2 * QP][2][PRE_N];         // per pair slot and half: one-argument transcendental values (eval_half, FIX)
     unsigned short live[2][2][QP * 168];  // per group and direction: full tasks from the front, erbl-only from the back
@@ -225,7 +225,7 @@ assemble_cst_pair_kernel(int ca, int cb, int n, int nxi, const double* __restric
                 cls[3] = task_class(yy2, xx2, safe);
 #pragma unroll
                 for (int k = 0; k < 4; k++)
-                    if (cls[k] == 0) { sh.hv[ps][set][4 * node + k][0] = 0.0; sh.hv[ps][set][4 * node + k][1] = 0.0; }
+                    if (cls[k] == 0) { sh.hv[ps][set][0][42 * k + node] = 0.0; sh.hv[ps][set][1][42 * k + node] = 0.0; }
                 // one-argument transcendental values of a slot that starts in this round, from the per-row table
                 if (node == 0 && set == 0 && S.nint == 1) {
                     const double* rowtab = d_pre_tab + (size_t)(S.inst / 3ULL) * PRE_ROW;
@@ -302,8 +302,8 @@ assemble_cst_pair_kernel(int ca, int cb, int n, int nxi, const double* __restric
                 double out[NKERN];
                 if (seg < 2) eval_half<MASK, true, 3>(X, Y, Xo, Yo, out, preS, preO, dir ? 2 : 1);
                 else eval_half<MASK, false, 3>(X, Y, Xo, Yo, out, preS, preO, dir ? 2 : 1);
-                sh.hv[ps][set][task][0] = out[KA];
-                sh.hv[ps][set][task][1] = out[KB];
+                sh.hv[ps][set][0][42 * (task & 3) + node] = out[KA];
+                sh.hv[ps][set][1][42 * (task & 3) + node] = out[KB];
             }
         }
 #ifdef TKB_K2_STATS
@@ -322,9 +322,9 @@ assemble_cst_pair_kernel(int ca, int cb, int n, int nxi, const double* __restric
             const QSlot& S = sh.slot[2 * ps + st];
             if (node < 21 * S.nint) {
                 const int set = (st == 0) ? 0 : ((sh.same[ps] || sh.own0[ps]) ? 0 : 1);
-                const double (*h)[2] = sh.hv[ps][set] + 4 * node;
-                const double Kxy = st ? combine_halves<KB>(h[0][1], h[1][1], S.xi) : combine_halves<KA>(h[0][0], h[1][0], S.xi);
-                const double Kyx = st ? combine_halves<KB>(h[2][1], h[3][1], S.xi) : combine_halves<KA>(h[2][0], h[3][0], S.xi);
+                const double* h = sh.hv[ps][set][st] + node;
+                const double Kxy = st ? combine_halves<KB>(h[0], h[42], S.xi) : combine_halves<KA>(h[0], h[42], S.xi);
+                const double Kyx = st ? combine_halves<KB>(h[84], h[126], S.xi) : combine_halves<KA>(h[84], h[126], S.xi);
                 sh.fv[2 * ps + st][node] = Kxy - Kyx;
             }
         }

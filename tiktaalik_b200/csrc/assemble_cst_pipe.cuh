@@ -24,7 +24,7 @@ struct QPipeShared {
     QSlot slot[2 * QG];
     QHead head[2 * QG];
     double ny[2 * QG][42][2];
-    double hv[2 * QG][168];
+    double hv[2 * QG][168];             // [instance][42 (2 dir + half) + node]: half-kernel values (the K pass reads consecutive nodes)
     double fv[2 * QG][42];
     double pre[2 * QG][2][PRE_N];       // per instance and half: one-argument transcendental values (eval_half, FIX)
     unsigned short live[2][2][QG * 84]; // per group and direction: full tasks from the front, erbl-only from the back
@@ -290,7 +290,7 @@ assemble_cst_pipe_kernel(int c, int n, int nxi, const double* __restrict__ xi_ar
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
                     if (!HAS_ERBL && cls[k] == 1) cls[k] = 0;
-                    if (cls[k] == 0) sh.hv[s][4 * node + k] = 0.0;
+                    if (cls[k] == 0) sh.hv[s][42 * k + node] = 0.0;
                 }
             }
             const int elane_ = etid & 31;
@@ -374,7 +374,7 @@ assemble_cst_pipe_kernel(int c, int n, int nxi, const double* __restrict__ xi_ar
                 double out[NKERN];
                 if (seg < 2) eval_half<bit(KID), true, 3>(X, Y, Xo, Yo, out, preS, preO, dir ? 2 : 1);
                 else eval_half<bit(KID), false, 3>(X, Y, Xo, Yo, out, preS, preO, dir ? 2 : 1);
-                sh.hv[s][task] = out[KID];
+                sh.hv[s][42 * (task & 3) + node] = out[KID];
             }
         }
         qp_bar_sync(QP_BAR_EV, NE);
@@ -388,9 +388,9 @@ assemble_cst_pipe_kernel(int c, int n, int nxi, const double* __restrict__ xi_ar
             const int s = g * QG + e / 42, node = e % 42;
             const QSlot& S = sh.slot[s];
             if (node < 21 * S.nint) {
-                const double* h = sh.hv[s] + 4 * node;
-                const double Kxy = combine_halves<KID>(h[0], h[1], S.xi);
-                const double Kyx = combine_halves<KID>(h[2], h[3], S.xi);
+                const double* h = sh.hv[s] + node;
+                const double Kxy = combine_halves<KID>(h[0], h[42], S.xi);
+                const double Kyx = combine_halves<KID>(h[84], h[126], S.xi);
                 sh.fv[s][node] = Kxy - Kyx;
             }
         }
