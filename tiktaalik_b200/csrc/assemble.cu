@@ -116,6 +116,7 @@ struct K1Shared {
     double pre[K1_ROWS][2][PRE_N];        // one-argument logs/dilogs of the row's fixed point (eval_half, FIX = 1)
     double w[6];                          // Lagrange weights (the same for every row)
     int iS[K1_ROWS][NNODE];               // stencil origins (1-based)
+    int jlo[K1_ROWS][6], jhi[K1_ROWS][6]; // per integration interval: smallest / largest stencil origin of its 21 nodes
     int iSx[K1_ROWS];
     int allfinite[K1_ROWS];
     int nlive;
@@ -225,6 +226,18 @@ assemble_fixed_kernel(int n, int nxi, const double* __restrict__ xi_arr, int gri
     }
     __syncthreads();
     K1_CLK(1);
+    // range of columns an interval's nodes touch (phase 2 skips the other intervals of an ordinary column)
+    if (tid < nrows * 6) {
+        const int r = tid / 6, iv = tid - 6 * r;
+        int lo = sh.iS[r][21 * iv], hi = lo;
+        for (int q = 1; q < 21; q++) {
+            const int v = sh.iS[r][21 * iv + q];
+            lo = v < lo ? v : lo;
+            hi = v > hi ? v : hi;
+        }
+        sh.jlo[r][iv] = lo;
+        sh.jhi[r][iv] = hi;
+    }
     // ---- phase 1b: the live halves, all 22 kernels each, in eight passes of two or three kernels ----
     // One evaluation of all 22 kernels is ~100 KB of straight-line code; as a single pass every warp streamed it from
     // L2 on its own (the warps drift apart by more than the instruction cache holds).  Here the transcendental values
@@ -373,8 +386,10 @@ assemble_fixed_kernel(int n, int nxi, const double* __restrict__ xi_arr, int gri
             double resk[NKERN];
 #pragma unroll
             for (int f = 0; f < NKERN; f++) resk[f] = 0.0;
+            // an ordinary column (f_j(x_i) = 0) outside the interval's stencils gets exact zeros from all 21 nodes
+            const bool touched = dense || fx != 0.0 || (j >= sh.jlo[r][iv] && j <= sh.jhi[r][iv] + 5);
             // qk21 order: centre (weight wgk(11)), then t = 2,4,..,10, then t = 1,3,..,9
-            for (int s = 0; s <= 10; s++) {
+            for (int s = 0; touched && s <= 10; s++) {
                 const int tt = (s == 0) ? 11 : ((s <= 5) ? 2 * s : 2 * (s - 5) - 1);
                 const int k1 = 21 * iv + ((s == 0) ? 0 : 2 * tt - 1);
                 const int k2 = k1 + 1;                       // unused for the centre
@@ -1076,13 +1091,13 @@ template <int KA, int KB>
 static int launch_pair_one(int ca, int cb, int n, int nxi, const double* xi_dev, int grid_type, QLists* lists, int sms,
                            unsigned long long* counter, double* cst_res, int* cst_last, int* cst_ifail, cudaStream_t st)
 {
-    constexpr int QP = TKB_QPP, NT = 768;
+    constexpr int QP = TKB_QPP, NT = TKB_QPT, BPS = TKB_QPBPS;
     const size_t smem = sizeof(QPairShared<QP>);
-    auto kern = assemble_cst_pair_kernel<KA, KB, QP, NT>;
+    auto kern = assemble_cst_pair_kernel<KA, KB, QP, NT, BPS>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
     const unsigned long long total = (unsigned long long)nxi * n * 3ULL;
-    long long nb = (long long)sms;
+    long long nb = (long long)sms * BPS;
     const long long want = (long long)((total + 2 * QP - 1) / (2 * QP));
     if (nb > want) nb = want;
     kern<<<(int)nb, NT, smem, st>>>(ca, cb, n, nxi, xi_dev, grid_type, lists, counter, cst_res, cst_last, cst_ifail);

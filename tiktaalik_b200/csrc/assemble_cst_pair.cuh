@@ -31,8 +31,8 @@ struct QPairShared {
     unsigned char own0[2 * QP];           // state whose request node set 0 carries (0: state A, 1: state B alone)
 };
 
-template <int KA, int KB, int QP, int NT>
-__global__ void __launch_bounds__(NT, 1)
+template <int KA, int KB, int QP, int NT, int BPS = 1>
+__global__ void __launch_bounds__(NT, BPS)
 assemble_cst_pair_kernel(int ca, int cb, int n, int nxi, const double* __restrict__ xi_arr, int grid_type,
                          QLists* __restrict__ lists, unsigned long long* __restrict__ counter,
                          double* __restrict__ cst_res, int* __restrict__ cst_last, int* __restrict__ cst_ifail)
