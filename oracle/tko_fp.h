@@ -17,8 +17,9 @@
  *   - log: the classic fdlibm/musl reduction  x = 2^k (1+f), s = f/(2+f),
  *     log(1+f) = f - hfsq + s (hfsq + R(s^2)), degree-14 minimax R (Lg1..Lg7);
  *     error < 1 ulp.
- *   - pow(x>0, y): double-double log (two-sum + fma residuals), exact product
- *     with y, fdlibm-style exp of the hi/lo pair; error ~ 1 ulp.
+ *   - pow(x>0, y): table-driven double-double log, exact product with y, table-driven
+ *     exponential of the hi/lo pair with one final rounding: correctly rounded in
+ *     practice (see the comment above tko_log_dd).
  * Compile with -ffp-contract=off (no implicit FMA) and without -ffast-math.
  */
 #ifndef TKO_FP_H
@@ -99,41 +100,55 @@ static inline double tko_log(double x)
     return fma(dk, TKO_LN2_HI, f - (hfsq - u));
 }
 
-/* log(x) = hi + lo with ~2^-60 relative accuracy, x positive finite non-zero */
+/* ---- pow: table-driven, double-double intermediates (tables: tko_pow_tables.h, tools/make_pow_tables.py) ----
+ * The grid-type-2 node map is x = +-(xi^2)^(1 -+ eta) (gridspace.f90:36-41): every node of the outer halves of the grid
+ * is a pow result, so pow has to return what the libm behind a real build returns.  glibc's pow is correctly rounded in
+ * all but ~0.1 % of the cases; a ~0.6 ulp pow (the fdlibm-style one used until round 2) disagrees with it in 10 %.
+ * This one keeps ~2^-70 relative accuracy in the logarithm and ~2^-70 in the exponential before the single final
+ * rounding, i.e. it is correctly rounded except when the exact result lies within ~2^-11 ulp of a rounding boundary.
+ *   log x = k ln2 + L_i + log1p(rho),  x = 2^k m,  i = round(128 m) - 90,  rho = m invc_i - 1 EXACTLY as a + b
+ *           (a = fl(m invc) - 1, b = the fma residual of the product),  L_i = -log(invc_i) tabulated as hi + lo;
+ *           log1p(rho) = a - a^2/2 (exact product) + [b - a b + a^3 (1/3 - a/4 + ... - a^7/10)];  all large pieces are
+ *           added with error-free two-sums, the small ones collected in one double.
+ *   p = y log x as an exact product of y with the hi part plus y times the lo part.
+ *   exp p = 2^e T_j (1 + expm1(r)),  128 p / ln2 = 128 e + j + (128 / ln2) r,  |r| <= ln2 / 256,  T_j = 2^(j/128) as hi + lo,
+ *           expm1(r) = r + r^2/2 + ... + r^6/720 with r = rh + rl; T_j rh is formed exactly (fma), the rest in one double.
+ * The CUDA side (tkb_fp.cuh: pow_) performs the same operations in the same order on the same tables. */
+#include "tko_pow_tables.h"
+
+static inline void tko_two_sum(double a, double b, double *s, double *e)   /* Knuth: a + b = s + e exactly */
+{
+    double t = a + b;
+    double bb = t - a;
+    *e = (a - (t - bb)) + (b - bb);
+    *s = t;
+}
+
+/* log(x) = hi + lo, x positive finite non-zero; ~2^-70 relative */
 static inline void tko_log_dd(double x, double *hi, double *lo)
 {
     int k;
     double m = tko_log_reduce(x, &k);
-    double f = m - 1.0;                               /* exact */
-    double d = 2.0 + f;
-    double dl = f - (d - 2.0);                        /* exact: d + dl = 2 + f */
-    double sh = f / d;
-    double r = fma(-sh, d, f);
-    r = r - sh * dl;
-    double sl = r / d;                                /* s = sh + sl */
-    double z = sh * sh;
-    double w = z * z;
-    double t1 = w * (TKO_LG2 + w * (TKO_LG4 + w * TKO_LG6));
-    double t2 = z * (TKO_LG1 + w * (TKO_LG3 + w * (TKO_LG5 + w * TKO_LG7)));
-    double R = t2 + t1;                               /* log(m) = 2 s + s R */
+    int i = (int)(m * 128.0 + 0.5) - 90;              /* m*128 exact; 0 <= i <= 92 */
+    double invc = TKO_POW_LOG[i][0];
+    double ph = m * invc;
+    double b = fma(m, invc, -ph);                     /* m invc = ph + b exactly */
+    double a = ph - 1.0;                              /* exact (ph within [1/2, 2]) */
+    double sqh = a * a;
+    double sql = fma(a, a, -sqh);                     /* a^2 = sqh + sql exactly */
+    double q = 1.0 / 3.0 + a * (-0.25 + a * (0.2 + a * (-1.0 / 6.0 + a * (1.0 / 7.0 + a * (-0.125 + a * (1.0 / 9.0 + a * -0.1))))));
+    double t = (a * sqh) * q;                         /* a^3/3 - a^4/4 + ... - a^10/10 */
     double dk = (double)k;
-    double A = dk * TKO_LN2_HI;                       /* exact */
-    double B = 2.0 * sh;
-    double h = A + B;                                 /* two-sum (Knuth) */
-    double bb = h - A;
-    double l = (A - (h - bb)) + (B - bb);
-    double tail = l + ((2.0 * sl + sh * R) + dk * TKO_LN2_LO);
-    double H = h + tail;
-    *lo = tail - (H - h);
+    double h1, e1, h2, e2, h3, e3, h4, e4;
+    tko_two_sum(dk * TKO_LN2_HI, TKO_POW_LOG[i][1], &h1, &e1);   /* k LN2_HI is exact (33 significant bits) */
+    tko_two_sum(h1, a, &h2, &e2);
+    tko_two_sum(h2, -0.5 * sqh, &h3, &e3);
+    tko_two_sum(h3, t, &h4, &e4);
+    double low = ((e1 + e2) + (e3 + e4)) + ((dk * TKO_LN2_LO + TKO_POW_LOG[i][2]) + ((b - a * b) - 0.5 * sql));
+    double H = h4 + low;
+    *lo = low - (H - h4);
     *hi = H;
 }
-
-static const double TKO_INVLN2 = 1.44269504088896338700e+00;
-static const double TKO_EP1 =  1.66666666666666019037e-01;
-static const double TKO_EP2 = -2.77777777770155933842e-03;
-static const double TKO_EP3 =  6.61375632143793436117e-05;
-static const double TKO_EP4 = -1.65339022054652515390e-06;
-static const double TKO_EP5 =  4.13813679705723846039e-08;
 
 /* exp(ph + pl), |pl| << |ph| */
 static inline double tko_exp_dd(double ph, double pl)
@@ -141,14 +156,21 @@ static inline double tko_exp_dd(double ph, double pl)
     if (ph != ph) return ph;
     if (ph > 709.782712893384) return TKO_INF;
     if (ph < -745.2) return 0.0;
-    double kf = floor(ph * TKO_INVLN2 + 0.5);
-    double hi = ph - kf * TKO_LN2_HI;
-    double lo = kf * TKO_LN2_LO - pl;
-    double r = hi - lo;
-    double t = r * r;
-    double c = r - t * (TKO_EP1 + t * (TKO_EP2 + t * (TKO_EP3 + t * (TKO_EP4 + t * TKO_EP5))));
-    double y = 1.0 - ((lo - (r * c) / (2.0 - c)) - hi);
-    int k = (int)kf;
+    double kf = floor(ph * TKO_POW_INV_LN2_128 + 0.5);
+    double rh0 = ph - kf * (TKO_LN2_HI * 0.0078125);  /* exact: kf LN2_HI / 128 has < 53 bits, Sterbenz */
+    double rl0 = pl - kf * (TKO_LN2_LO * 0.0078125);
+    double rh, rl;
+    tko_two_sum(rh0, rl0, &rh, &rl);
+    int kk = (int)kf;
+    int j = kk & 127;
+    int k = (kk - j) / 128;
+    double Th = TKO_POW_EXP[j][0], Tl = TKO_POW_EXP[j][1];
+    double ql = rl + (rh * rh) * (0.5 + rh * (1.0 / 6.0 + rh * (1.0 / 24.0 + rh * (1.0 / 120.0 + rh * (1.0 / 720.0)))));
+    double p1 = Th * rh;
+    double p1l = fma(Th, rh, -p1);                    /* Th rh = p1 + p1l exactly */
+    double s, e;
+    tko_two_sum(Th, p1, &s, &e);
+    double y = s + ((e + p1l) + (Tl + (Th * ql + Tl * rh)));
     if (k > 1023) {                                   /* y*2^k may still be finite */
         y = y * tko_from_bits((uint64_t)(1023 + 1023) << 52);
         k -= 1023;
@@ -181,8 +203,7 @@ static inline double tko_pow(double x, double y)
 
 /* x**1.5 as QUADPACK's error estimate needs it (integration.f90, qk21: (200*abserr/resasc)**1.5_dp under min(1, .)).
  * For 1e-150 < t < 1:  sqrt(t) = s + e with e from the exact residual t - s*s, so t**1.5 = t*s + t*e to ~2^-104:
- * correctly rounded in practice, like the libm pow behind the reference (tko_pow is good to ~0.6 ulp only, and
- * far more expensive).  t >= 1 gives a value >= 1, which min(1, .) turns into 1.  Everything else (NaN, zero,
+ * correctly rounded in practice, like the libm pow behind the reference (and far cheaper than tko_pow).  t >= 1 gives a value >= 1, which min(1, .) turns into 1.  Everything else (NaN, zero,
  * below 1e-150) goes through tko_pow. */
 static inline double tko_pow15_capped(double t)
 {
