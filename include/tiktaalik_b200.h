@@ -177,7 +177,7 @@ int tkb_eval_integrand(int c, int npts, const double* x_dev, const double* y_dev
  * an exact zero */
 int tkb_task_classes(int c, int npts, const double* x_dev, const double* y_dev, const double* xi_dev, int* cls_dev,
                      double* full_dev, double* erbl_dev, void* stream);
-/* which = 0 log(a), 1 pow(a,b), 2 dilog(a) with the library's own device arithmetic */
+/* which = 0 log(a) (kernels), 1 pow(a,b), 2 dilog(a), 3 log(a) of the grid maps (correctly rounded in practice), with the library's own device arithmetic */
 int tkb_eval_scalar(int which, int npts, const double* a_dev, const double* b_dev, double* out_dev, void* stream);
 /* device time in ms of the stages of the last tkb_make_kernels / tkb_make_matrices:
  * ms[0] fixed quadrature, ms[1] QAGS constants, ms[2] RK4 stepping (incl. composition) */

@@ -99,6 +99,7 @@ double tko_grid_node(int i, int nx, double xi, int grid_type);       /* convolut
 /* test hooks for the primitives of tko_fp.h */
 double tko_log_x(double x);
 double tko_pow_x(double x, double y);
+double tko_log_cr_x(double x);   /* the grid maps' logarithm (correctly rounded in practice) */
 
 /* ---- integration.f90 ---- */
 void tko_qk21(tko_f1 f, void *ctx, double a, double b,

@@ -53,7 +53,7 @@ def lib():
         L = C.CDLL(build())
         d, i = C.c_double, C.c_int
         sigs = {
-            "tko_dilog": (d, [d]), "tko_log_x": (d, [d]), "tko_pow_x": (d, [d, d]), "tko_theta_step": (d, [d]), "tko_rho_step": (d, [d, d]),
+            "tko_dilog": (d, [d]), "tko_log_x": (d, [d]), "tko_log_cr_x": (d, [d]), "tko_pow_x": (d, [d, d]), "tko_theta_step": (d, [d]), "tko_rho_step": (d, [d, d]),
             "tko_erbl_step": (d, [d]), "tko_abslog": (d, [d]), "tko_log2": (d, [d]), "tko_logprod": (d, [d, d]),
             "tko_kernel_by_index": (d, [i, d, d, d]),
             "tko_cst_integral": (d, [i, d, d, _ip, _ip]),

@@ -150,6 +150,20 @@ static inline void tko_log_dd(double x, double *hi, double *lo)
     *hi = H;
 }
 
+/* log(x) from the double-double logarithm: correctly rounded in practice.  For the grid maps (gridspace.f90:49-61,
+ * 95-99: eta = log(|x| / xi^2) / (2 log xi), Jacobian 2 log(xi) (xi^2)^(1 -+ eta)), where the value behind a real build
+ * is libm's; the kernels' logarithms keep the cheaper tko_log. */
+static inline double tko_log_cr(double x)
+{
+    uint64_t ix = tko_bits(x);
+    if ((ix << 1) == 0) return -TKO_INF;
+    if (ix >> 63) return TKO_NAN;
+    if ((ix >> 52) >= 0x7ff) return x;
+    double hi, lo;
+    tko_log_dd(x, &hi, &lo);
+    return hi;
+}
+
 /* exp(ph + pl), |pl| << |ph| */
 static inline double tko_exp_dd(double ph, double pl)
 {
@@ -225,6 +239,7 @@ static inline double tko_pow15_capped(double t)
  * last bits (and QUADPACK may take a few more or fewer bisections); it is never used as a checker. */
 #ifdef TKO_LIBM
 #define tko_log(x) log(x)
+#define tko_log_cr(x) log(x)
 #define tko_pow(x, y) pow((x), (y))
 #define tko_pow15_capped(t) (((t) >= 1.0) ? 1.0 : pow((t), 1.5))
 #endif

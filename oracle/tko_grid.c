@@ -36,9 +36,9 @@ double tko_pull_back(double x, double xi, int nx, int grid_type)
     double eta;
     switch (grid_type) {
     case 2:
-        if (x < -xi) eta = 0.5 * tko_log(-x / (xi * xi)) / tko_log(xi);
+        if (x < -xi) eta = 0.5 * tko_log_cr(-x / (xi * xi)) / tko_log_cr(xi);
         else if (x <= xi) eta = 0.5 * x / xi;
-        else eta = 0.5 * tko_log((xi * xi) / x) / tko_log(xi);
+        else eta = 0.5 * tko_log_cr((xi * xi) / x) / tko_log_cr(xi);
         break;
     case 1:
     default:
@@ -54,9 +54,9 @@ double tko_push_jacob(double eta, double xi, int nx, int grid_type)
     double J;
     switch (grid_type) {
     case 2:
-        if (eta < -0.5) J = -tko_pow(xi * xi, 1.0 + eta) * 2.0 * tko_log(xi);
+        if (eta < -0.5) J = -tko_pow(xi * xi, 1.0 + eta) * 2.0 * tko_log_cr(xi);
         else if (eta <= 0.5) J = 2.0 * xi;
-        else J = -tko_pow(xi * xi, 1.0 - eta) * 2.0 * tko_log(xi);
+        else J = -tko_pow(xi * xi, 1.0 - eta) * 2.0 * tko_log_cr(xi);
         break;
     case 1:
     default:
@@ -156,4 +156,5 @@ void tko_pixelspace(int nx, double xi, int grid_type, double *x)
 
 /* test hooks: the primitives of tko_fp.h as exported symbols */
 double tko_log_x(double x) { return tko_log(x); }
+double tko_log_cr_x(double x) { return tko_log_cr(x); }
 double tko_pow_x(double x, double y) { return tko_pow(x, y); }

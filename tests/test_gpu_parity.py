@@ -71,6 +71,20 @@ def test_log_pow_bit_identical_to_oracle(tk, tko):
     got = _eval_scalar(tk, 1, base, expo)
     ref = np.array([L.tko_pow_x(float(b), float(e)) for b, e in zip(base, expo)])
     assert np.array_equal(bits(got), bits(ref))
+    # the grid-type-2 node maps themselves, extreme exponents, and the grid maps' own logarithm
+    nodes = (np.float32(2 * np.arange(1, 321) - 1) / np.float32(320) - np.float32(1)).astype(np.float64)
+    xi = np.geomspace(2e-5, 0.9, 200)
+    base = np.repeat(xi * xi, nodes.size)
+    expo = np.tile(1.0 - np.abs(nodes), xi.size)
+    base = np.concatenate([base, [1e-300, 1e300, 2.0, 2.0, 0.5, 1 + 2.0 ** -52, 5e-324, 10.0, 10.0]])
+    expo = np.concatenate([expo, [1.05, 1.02, 1023.5, -1074.0, 1074.5, 2.0 ** 40, 0.5, 400.0, -400.0]])
+    got = _eval_scalar(tk, 1, base, expo)
+    ref = np.array([L.tko_pow_x(float(b), float(e)) for b, e in zip(base, expo)])
+    assert np.array_equal(bits(got), bits(ref))
+    got = _eval_scalar(tk, 3, x)
+    ref = np.array([L.tko_log_cr_x(float(v)) for v in x])
+    assert np.array_equal(bits(got)[~np.isnan(ref)], bits(ref)[~np.isnan(ref)])
+    assert np.array_equal(np.isnan(got), np.isnan(ref))
 
 
 def test_dilog_bit_identical_to_oracle(tk, tko):

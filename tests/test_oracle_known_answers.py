@@ -457,6 +457,12 @@ def test_pow_is_correctly_rounded(tko):
             assert abs(got - want) <= math.ulp(want)
     assert bad == 0, bad
     assert L.tko_pow_x(2.0, -1074.0) == 5e-324 and L.tko_pow_x(0.5, 1074.5) == 5e-324      # gradual underflow (as glibc)
+    # the grid maps' logarithm (pull_back, push_jacob): the hi part of the same double-double logarithm
+    xs = np.concatenate([np.exp(rng.uniform(-30, 30, 3000)), rng.uniform(1e-6, 2, 3000), np.geomspace(2e-5, 0.9, 500),
+                         1 + rng.uniform(-1e-6, 1e-6, 300), np.exp(rng.uniform(-740, 700, 300)), [5e-324, 1e-310]])
+    for v in xs:
+        assert L.tko_log_cr_x(float(v)) == float(mp.log(mp.mpf(float(v)))), v
+    assert L.tko_log_cr_x(1.0) == 0.0 and L.tko_log_cr_x(0.0) == -np.inf and np.isnan(L.tko_log_cr_x(-1.0))
     assert L.tko_pow_x(10.0, 400.0) == np.inf and L.tko_pow_x(10.0, -400.0) == 0.0
 
 

@@ -840,6 +840,7 @@ __global__ void eval_scalar_kernel(int which, int npts, const double* __restrict
     case 0: out[p] = log_(a[p]); break;
     case 1: out[p] = pow_(a[p], b[p]); break;
     case 2: out[p] = dilog(a[p]); break;
+    case 3: out[p] = log_cr(a[p]); break;
     }
 }
 

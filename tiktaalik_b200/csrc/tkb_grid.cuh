@@ -32,9 +32,9 @@ TKB_DEV double push_forward(double eta, double xi, int grid_type)
 TKB_DEV double pull_back(double x, double xi, int grid_type)
 {
     if (grid_type == 2) {
-        if (x < -xi) return 0.5 * log_(-x / (xi * xi)) / log_(xi);
+        if (x < -xi) return 0.5 * log_cr(-x / (xi * xi)) / log_cr(xi);
         if (x <= xi) return 0.5 * x / xi;
-        return 0.5 * log_((xi * xi) / x) / log_(xi);
+        return 0.5 * log_cr((xi * xi) / x) / log_cr(xi);
     }
     return x;
 }
@@ -42,9 +42,9 @@ TKB_DEV double pull_back(double x, double xi, int grid_type)
 TKB_DEV double push_jacob(double eta, double xi, int grid_type)
 {
     if (grid_type == 2) {
-        if (eta < -0.5) return -pow_(xi * xi, 1.0 + eta) * 2.0 * log_(xi);
+        if (eta < -0.5) return -pow_(xi * xi, 1.0 + eta) * 2.0 * log_cr(xi);
         if (eta <= 0.5) return 2.0 * xi;
-        return -pow_(xi * xi, 1.0 - eta) * 2.0 * log_(xi);
+        return -pow_(xi * xi, 1.0 - eta) * 2.0 * log_cr(xi);
     }
     return 1.0;
 }
