@@ -14,9 +14,9 @@
  * CUDA path (tiktaalik_b200/csrc/tkb_fp.cuh, written separately) implement the
  * SAME published algorithms with the SAME operation order using only IEEE-754
  * correctly rounded operations (+ - * / sqrt fma):
- *   - log: the classic fdlibm/musl reduction  x = 2^k (1+f), s = f/(2+f),
- *     log(1+f) = f - hfsq + s (hfsq + R(s^2)), degree-14 minimax R (Lg1..Lg7);
- *     error < 1 ulp.
+ *   - log: table-driven, x = 2^k m, rho = m invc_i - 1 formed exactly, L_i = -log(invc_i)
+ *     tabulated as hi + lo, error-free sums of the large pieces, one final rounding:
+ *     correctly rounded in practice (see the comment above tko_log_core).
  *   - pow(x>0, y): table-driven double-double log, exact product with y, table-driven
  *     exponential of the hi/lo pair with one final rounding: correctly rounded in
  *     practice (see the comment above tko_log_dd).
@@ -48,13 +48,6 @@ static inline double tko_max(double a, double b) { return (a > b) ? a : b; }
 
 static const double TKO_LN2_HI = 6.93147180369123816490e-01; /* 0x3fe62e42fee00000 */
 static const double TKO_LN2_LO = 1.90821492927058770002e-10; /* 0x3dea39ef35793c76 */
-static const double TKO_LG1 = 6.666666666666735130e-01;
-static const double TKO_LG2 = 3.999999999940941908e-01;
-static const double TKO_LG3 = 2.857142874366239149e-01;
-static const double TKO_LG4 = 2.222219843214978396e-01;
-static const double TKO_LG5 = 1.818357216161805012e-01;
-static const double TKO_LG6 = 1.531383769920937332e-01;
-static const double TKO_LG7 = 1.479819860511658591e-01;
 
 /* Argument reduction shared by log and log_dd: returns k and m in [sqrt(1/2), sqrt(2))
  * with x = 2^k m.  x must be positive, finite and non-zero on entry. */
@@ -77,27 +70,51 @@ static inline double tko_log_reduce(double x, int *kout)
     return tko_from_bits(ix);
 }
 
+/* log: table-driven (tko_pow_tables.h), ~2^-63 relative before the one final rounding: 0.002 % of the logarithms of
+ * arguments in (0, 2) and 0.03 % of those within 1e-2 of 1 differ from the correctly rounded value -- glibc's log, which a
+ * real build of the reference calls, misses 0.1 % / 0.02 %.  Rounds 1-2 used fdlibm's algorithm (< 1 ulp, but 7.6 % of the
+ * logarithms of arguments in (0, 2) one ulp off).
+ *   x = 2^k m, m in [sqrt(1/2), sqrt(2)); 129 intervals of 2^13 steps of m's high word, placed so that m = 1 is the centre c
+ *   of its interval (log c = 0 and rho = m - 1 exactly there), c = the midpoint elsewhere; invc_i = 1 / c_i to 21 bits (a high
+ *   word), L_i = -log(invc_i) as a double + a high-word correction: a 16-byte entry; rho = m invc_i - 1 = a + b exactly (b = the
+ *   fma residual), |rho| <= 2^-8,
+ *   log x = [k LN2_HI + L_i.hi + a]  (error-free fast two-sums: every partial sum dominates the next term)
+ *         + [two-sum errors + k LN2_LO + L_i.lo + b (1 - a) - a^2/2 + a^3/3 - a^4/4 + ... - a^8/8].
+ * The CUDA side (tkb_fp.cuh: log_core) performs the same operations in the same order. */
+#include "tko_pow_tables.h"
+
+static inline double tko_log_core(double m, int k)
+{
+    uint32_t i = ((uint32_t)(tko_bits(m) >> 32) - 0x3fe6a09eu + 0x109eu) >> 13;      /* 0 <= i <= 128 */
+    double invc = tko_from_bits((uint64_t)TKO_LOG_TAB[i].invc_hi << 32);
+    double Lh = TKO_LOG_TAB[i].Lh;
+    double Ll = tko_from_bits((uint64_t)TKO_LOG_TAB[i].Ll_hi << 32);
+    double ph = m * invc;
+    double b = fma(m, invc, -ph);
+    double a = ph - 1.0;
+    double sqh = a * a;
+    /* a^3 (1/3 - a/4 + a^2/5 - a^3/6 + a^4/7 - a^5/8) */
+    double q = fma(a, fma(a, fma(a, fma(a, fma(a, -0.125, 1.0 / 7.0), -1.0 / 6.0), 0.2), -0.25), 1.0 / 3.0);
+    double t = (a * sqh) * q;
+    double dk = (double)k;
+    double A = dk * TKO_LN2_HI;                       /* exact: LN2_HI has 33 significant bits */
+    double h1 = A + Lh;
+    double e1 = Lh - (h1 - A);                        /* fast two-sum: A = 0 or |A| >= 0.69 > |Lh| */
+    double h2 = h1 + a;
+    double e2 = a - (h2 - h1);                        /* h1 = 0 (k = 0, c = 1) or |h1| >= 0.0078 > |a| */
+    double low = (e1 + e2) + (fma(dk, TKO_LN2_LO, Ll) + (fma(-a, b, b) + fma(-0.5, sqh, t)));
+    return h2 + low;
+}
+
 static inline double tko_log(double x)
 {
     uint64_t ix = tko_bits(x);
     if ((ix << 1) == 0) return -TKO_INF;              /* log(+-0) = -inf  */
     if (ix >> 63) return TKO_NAN;                     /* log(negative)    */
     if ((ix >> 52) >= 0x7ff) return x;                /* +inf or NaN      */
-    if (ix == 0x3ff0000000000000ULL) return 0.0;
     int k;
     double m = tko_log_reduce(x, &k);
-    double f = m - 1.0;
-    double hfsq = 0.5 * f * f;
-    double s = f / (2.0 + f);
-    double z = s * s;
-    double w = z * z;
-    /* fdlibm e_log.c with the Horner steps and the final sums fused; the library's log_core fuses the same ones */
-    double t1 = w * fma(w, fma(w, TKO_LG6, TKO_LG4), TKO_LG2);
-    double t2 = z * fma(w, fma(w, fma(w, TKO_LG7, TKO_LG5), TKO_LG3), TKO_LG1);
-    double R = t2 + t1;
-    double dk = (double)k;
-    double u = fma(s, hfsq + R, dk * TKO_LN2_LO);
-    return fma(dk, TKO_LN2_HI, f - (hfsq - u));
+    return tko_log_core(m, k);
 }
 
 /* ---- pow: table-driven, double-double intermediates (tables: tko_pow_tables.h, tools/make_pow_tables.py) ----
@@ -114,8 +131,6 @@ static inline double tko_log(double x)
  *   exp p = 2^e T_j (1 + expm1(r)),  128 p / ln2 = 128 e + j + (128 / ln2) r,  |r| <= ln2 / 256,  T_j = 2^(j/128) as hi + lo,
  *           expm1(r) = r + r^2/2 + ... + r^6/720 with r = rh + rl; T_j rh is formed exactly (fma), the rest in one double.
  * The CUDA side (tkb_fp.cuh: pow_) performs the same operations in the same order on the same tables. */
-#include "tko_pow_tables.h"
-
 static inline void tko_two_sum(double a, double b, double *s, double *e)   /* Knuth: a + b = s + e exactly */
 {
     double t = a + b;
