@@ -73,6 +73,7 @@ __device__ const double* d_pre_tab = nullptr;
 
 __global__ void pre_table_kernel(int n, int nxi, const double* __restrict__ xi_arr, int grid_type, double* __restrict__ tab)
 {
+    log_tab_init();
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n * nxi * PRE_ROW) return;
     const int row = e / PRE_ROW, v = e - row * PRE_ROW;
@@ -129,6 +130,7 @@ assemble_fixed_kernel(int n, int nxi, const double* __restrict__ xi_arr, int gri
 {
     extern __shared__ __align__(16) unsigned char k1_smem[];
     K1Shared& sh = *reinterpret_cast<K1Shared*>(k1_smem);
+    log_tab_init();
     const int tid = threadIdx.x;
     const int ixi = blockIdx.y;
     const int i0 = blockIdx.x * K1_ROWS;           // 0-based first row of the block
@@ -820,6 +822,7 @@ __global__ void compose_kernel(int n, int nxi, int nfl, const double* __restrict
 __global__ void eval_kernels_kernel(int npts, const double* __restrict__ xs, const double* __restrict__ ys,
                                     const double* __restrict__ xis, double* __restrict__ out /*[npts][NKERN]*/)
 {
+    log_tab_init();
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= npts) return;
     const double x = xs[p], y = ys[p], xi = xis[p];
@@ -834,6 +837,7 @@ __global__ void eval_kernels_kernel(int npts, const double* __restrict__ xs, con
 __global__ void eval_scalar_kernel(int which, int npts, const double* __restrict__ a, const double* __restrict__ b,
                                    double* __restrict__ out)
 {
+    log_tab_init();
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= npts) return;
     switch (which) {
@@ -853,6 +857,7 @@ template <int KID>
 __global__ void eval_integrand_kernel(int npts, const double* __restrict__ xs, const double* __restrict__ ys,
                                       const double* __restrict__ xis, double* __restrict__ out)
 {
+    log_tab_init();
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= npts) return;
     const double x = xs[p], y = ys[p], xi = xis[p];
@@ -898,6 +903,7 @@ __global__ void task_classes_kernel(int npts, const double* __restrict__ xs, con
                                     const double* __restrict__ xis, int* __restrict__ cls /*[npts][4]*/,
                                     double* __restrict__ full /*[npts][4]*/, double* __restrict__ erbl /*[npts][4]*/)
 {
+    log_tab_init();
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= npts) return;
     const double x = xs[p], y = ys[p], xi = xis[p];
@@ -923,6 +929,7 @@ __global__ void task_classes_all_kernel(int npts, const double* __restrict__ xs,
                                         const double* __restrict__ xis, int* __restrict__ cls,
                                         double* __restrict__ full, double* __restrict__ erbl)
 {
+    log_tab_init();
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= npts) return;
     const double x = xs[p], y = ys[p], xi = xis[p];

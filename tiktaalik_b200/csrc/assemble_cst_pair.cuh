@@ -44,6 +44,7 @@ assemble_cst_pair_kernel(int ca, int cb, int n, int nxi, const double* __restric
     constexpr unsigned MASK = bit(KA) | bit(KB);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     QPairShared<QP>& sh = *reinterpret_cast<QPairShared<QP>*>(smem_raw);
+    log_tab_init();
     const int tid = threadIdx.x;
     const unsigned long long total = (unsigned long long)nxi * n * 3ULL;
     if (tid < 4 * QP) { sh.slot[tid].nint = 0; sh.slot[tid].term = 0; sh.slot[tid].defer = 0; }

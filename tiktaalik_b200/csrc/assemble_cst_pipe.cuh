@@ -112,6 +112,7 @@ assemble_cst_pipe_kernel(int c, int n, int nxi, const double* __restrict__ xi_ar
     constexpr bool HAS_ERBL = (KID != K_NSN);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     QPipeShared<QG>& sh = *reinterpret_cast<QPipeShared<QG>*>(smem_raw);
+    log_tab_init();
     const int tid = threadIdx.x;
     const unsigned long long total = (unsigned long long)nxi * n * 3ULL;
     if (tid < 2 * QG) sh.slot[tid].nint = 0;

@@ -126,6 +126,7 @@ assemble_cst_queue_kernel(int c, int n, int nxi, const double* __restrict__ xi_a
     constexpr bool HAS_ERBL = (KID != K_NSN);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     QQueueShared<QG, NG>& sh = *reinterpret_cast<QQueueShared<QG, NG>*>(smem_raw);
+    log_tab_init();
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const unsigned long long total = (unsigned long long)nxi * n * 3ULL;
     if (tid < NI) sh.slot[tid].nint = 0;
