@@ -232,7 +232,7 @@ assemble_cst_pair_kernel(int ca, int cb, int n, int nxi, const double* __restric
                     const double* rowtab = d_pre_tab + (size_t)(S.inst / 3ULL) * PRE_ROW;
 #pragma unroll
                     for (int v = 0; v < 2 * PRE_N; v++)
-                        if ((qp_pre_need<KA>() >> (v % PRE_N)) & 1u) sh.pre[ps][v / PRE_N][v % PRE_N] = rowtab[v];
+                        if (((qp_pre_need<KA>() | qp_pre_need<KB>()) >> (v % PRE_N)) & 1u) sh.pre[ps][v / PRE_N][v % PRE_N] = rowtab[v];
                 }
             }
             const unsigned lt = (1u << elane) - 1u;
