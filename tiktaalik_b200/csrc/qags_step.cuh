@@ -11,7 +11,10 @@
 
 namespace tkb {
 
-constexpr int QHEAD = 48;            // list entries (1-based index < QHEAD) kept in shared memory
+#ifndef TKB_QHEAD
+#define TKB_QHEAD 48
+#endif
+constexpr int QHEAD = TKB_QHEAD;            // list entries (1-based index < QHEAD) kept in shared memory
 
 struct QSlot {                       // scalar QUADPACK state of one instance (integration.f90:374-381)
     double x, xi, xx1, xx2, a, b;

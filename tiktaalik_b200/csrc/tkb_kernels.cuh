@@ -95,7 +95,11 @@ TKB_DEV double dilog_at_half()
 // and one reduced dilogarithm, so the arguments are selected first and log_ / dilog_half are called
 // unconditionally -- lanes of a warp that fall into different ranges do not diverge.  Each range's
 // value is formed by exactly the reference's expression (specfun.f90:36-49).
+#ifdef TKB_DILOG_INLINE
+TKB_DEV double dilog(double z)
+#else
 static __device__ __noinline__ double dilog(double z)
+#endif
 {
     // range id: 0 z<-1, 1 -1<z<0, 2 z>2, 3 1<z<2, 4 1/2<z<1, 5 rational core (0<z<1/2, NaN), 6 special value
     int rg;
