@@ -147,3 +147,41 @@ def test_integration_document_names_every_c_abi_entry():
     names = sorted(set(re.findall(r"\b(tkb_[a-z0-9_]+)\s*\(", header)))
     assert len(names) > 25
     assert [n for n in names if n not in doc] == []
+
+
+def _table_literals(path, name):
+    """the hexadecimal literals of one table of a generated header, in order"""
+    txt = open(path).read()
+    body = txt[txt.index(name):]
+    body = body[body.index("{"):body.index("};")]
+    return re.findall(r"-?0x[0-9a-fA-F.]+(?:p[+-]?\d+)?", body)
+
+
+def test_log_pow_tables_are_the_same_on_both_sides():
+    """oracle/tko_pow_tables.h and tiktaalik_b200/csrc/tkb_pow_tables.cuh come from one generator (tools/make_pow_tables.py);
+    bit-identical log / pow on host and device needs bit-identical tables"""
+    c = os.path.join(ROOT, "oracle", "tko_pow_tables.h")
+    cu = os.path.join(ROOT, "tiktaalik_b200", "csrc", "tkb_pow_tables.cuh")
+    for cname, cuname, n in (("TKO_POW_LOG", "c_pow_log", 93 * 3), ("TKO_POW_EXP", "c_pow_exp", 128 * 2),
+                             ("TKO_LOG_TAB", "g_log_tab", 129 * 3)):
+        a, b = _table_literals(c, cname), _table_literals(cu, cuname)
+        assert len(a) == n and a == b, cname
+    inv = [re.search(r"INV_LN2_128 = (\S+);", open(p).read()).group(1) for p in (c, cu)]
+    assert inv[0] == inv[1]
+
+
+def test_log_pow_tables_regenerate_identically(tmp_path):
+    """the committed tables are what tools/make_pow_tables.py writes (needs mpmath)"""
+    pytest.importorskip("mpmath")
+    import importlib.util
+    import shutil
+    spec = importlib.util.spec_from_file_location("make_pow_tables", os.path.join(ROOT, "tools", "make_pow_tables.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    for sub in ("oracle", os.path.join("tiktaalik_b200", "csrc")):
+        os.makedirs(tmp_path / sub)
+    mod.ROOT = str(tmp_path)
+    mod.main()
+    for rel in (os.path.join("oracle", "tko_pow_tables.h"), os.path.join("tiktaalik_b200", "csrc", "tkb_pow_tables.cuh")):
+        assert open(tmp_path / rel).read() == open(os.path.join(ROOT, rel)).read(), rel
+    shutil.rmtree(tmp_path, ignore_errors=True)
