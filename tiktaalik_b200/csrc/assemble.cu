@@ -121,6 +121,7 @@ struct K1Shared {
     int iSx[K1_ROWS];
     int allfinite[K1_ROWS];
     int nlive;
+    int next2;                            // phase 2: next 32 items of the replay work list
     unsigned short live[K1_ROWS * 2 * NNODE];
 };
 
@@ -165,7 +166,7 @@ assemble_fixed_kernel(int n, int nxi, const double* __restrict__ xi_arr, int gri
                 sh.pre[r][v / PRE_N][v % PRE_N] = rowtab[v];
             }
         }
-        if (tid == 0) sh.nlive = 0;
+        if (tid == 0) { sh.nlive = 0; sh.next2 = 0; }
     }
     __syncthreads();
     {
@@ -304,22 +305,32 @@ assemble_fixed_kernel(int n, int nxi, const double* __restrict__ xi_arr, int gri
     // ---- phase 2: one thread per (row, column j); replay qk21 per interval in the reference's order ----
     const size_t fstride = (size_t)nxi * n * n;
     // The six columns whose basis function is non-zero at x_i carry the subtraction term f_j(x_i) of the plus
-    // kernels at every node (66 accumulation steps instead of the ~4 of an ordinary column).  They are split
-    // by kernel: one thread per (row, column, kernel pair), the pairs made of a plus-type and a regular kernel where
-    // possible so that every thread carries about the same work, and its two accumulation chains are independent.
-    // These 66-step items and the ordinary columns form ONE work list (heavy items first): as separate loops the
-    // 528 + 640 items of a block took four passes of 512 threads, two of them nearly empty, and the column replay
-    // was 58 % of the kernel.
+    // kernels at every node (66 accumulation steps instead of the ~4 of an ordinary column).  They are split by
+    // kernel pair (a plus-type and a regular kernel where possible: two independent accumulation chains of similar
+    // length) AND by integration interval: qk21's sum over the 21 nodes of an interval does not depend on the other
+    // intervals, so item (row, column, pair, interval) forms resk of its interval, parks it in the dead half of the value
+    // array, and a short second pass adds the six resk * hlgth in the reference's order (same operations, same order:
+    // bit-identical).  These 11-step items and the ordinary columns form ONE work list, ordinary columns (the heavier
+    // items) first, handed out 32 items at a time to whichever warp is free: as one 66-step item per thread the
+    // replay left a third of the threads waiting for the slowest (17 % of the kernel's warp time at the barrier).
     constexpr int NPAIR = NKERN / 2;
-    const int nspec = nrows * 6 * NPAIR;
-    for (int e = tid; e < nspec + nrows * n; e += K1_THREADS) {
-    if (e < nspec) {
-        const int r = e / (6 * NPAIR), t = e - r * 6 * NPAIR;
+    // the nine plus-type kernels 0, 5, 7, 8, 9, 18, 19, 20, 21 each with a regular one, then two regular pairs
+    constexpr int PA[NPAIR] = { K_K0QQ, K_A0GG, K_NSP, K_NSM, K_NSN, K_V1GG, K_A1GG, K_V1GGN, K_A1GGN, K_V1GQ, K_V1GQN };
+    constexpr int PB[NPAIR] = { K_A0QG, K_VMA0QG, K_A0GQ, K_VMA0GQ, K_VMA0GG, K_V1QQ, K_A1QQ, K_V1QG, K_A1QG, K_A1GQ, K_A1GQN };
+    const int nord = nrows * n, nspec = nrows * 6 * NPAIR;
+    for (;;) {
+    int base2 = 0;
+    if ((tid & 31) == 0) base2 = atomicAdd(&sh.next2, 32);
+    base2 = __shfl_sync(0xffffffffu, base2, 0);
+    if (base2 >= nord + 6 * nspec) break;
+    const int e = base2 + (tid & 31);
+    if (e >= nord + 6 * nspec) continue;
+    if (e >= nord) {
+        const int es = e - nord;
+        const int iv = es % 6, ep = es / 6;
+        const int r = ep / (6 * NPAIR), t = ep - r * 6 * NPAIR;
         if (sh.allfinite[r] == 0) continue;            // a NaN/Inf kernel value poisons every column (0*NaN): dense pass below
         const int jh = t / NPAIR, pr = t - NPAIR * jh;
-        // the nine plus-type kernels 0, 5, 7, 8, 9, 18, 19, 20, 21 each with a regular one, then two regular pairs
-        constexpr int PA[NPAIR] = { K_K0QQ, K_A0GG, K_NSP, K_NSM, K_NSN, K_V1GG, K_A1GG, K_V1GGN, K_A1GGN, K_V1GQ, K_V1GQN };
-        constexpr int PB[NPAIR] = { K_A0QG, K_VMA0QG, K_A0GQ, K_VMA0GQ, K_VMA0GG, K_V1QQ, K_A1QQ, K_V1QG, K_A1QG, K_A1GQ, K_A1GQN };
         int fa = PA[0], fb = PB[0];
 #pragma unroll
         for (int q = 1; q < NPAIR; q++)
@@ -329,51 +340,46 @@ assemble_fixed_kernel(int n, int nxi, const double* __restrict__ xi_arr, int gri
         if (fx == 0.0) continue;
         const double (*sK)[NNODE] = sh.H[r][0];
         const bool plusa = is_plus(fa), plusb = is_plus(fb);
-        double inta = 0.0, intb = 0.0;
-        for (int iv = 0; iv < 6; iv++) {
-            double reska = 0.0, reskb = 0.0;
-            for (int s = 0; s <= 10; s++) {
-                const int tt = (s == 0) ? 11 : ((s <= 5) ? 2 * s : 2 * (s - 5) - 1);
-                const int k1 = 21 * iv + ((s == 0) ? 0 : 2 * tt - 1);
-                const int k2 = k1 + 1;
-                const int m1 = j - sh.iS[r][k1];
-                const bool in1 = (m1 >= 0 && m1 < 6);
-                bool in2 = false;
-                int m2 = 0;
-                if (s != 0) { m2 = j - sh.iS[r][k2]; in2 = (m2 >= 0 && m2 < 6); }
-                const bool doa = plusa || in1 || in2, dob = plusb || in1 || in2;
-                if (!(doa || dob)) continue;
-                const double fy1 = in1 ? sh.b[r][k1][m1] : 0.0;
-                const double J1 = sh.J[r][k1];
-                const double w = c_wgk[tt];
-                if (s == 0) {
-                    if (doa) { const double fc = plusa ? (sK[fa][k1] * (fy1 - fx)) * J1 : (sK[fa][k1] * fy1) * J1; reska = w * fc; }
-                    if (dob) { const double fc = plusb ? (sK[fb][k1] * (fy1 - fx)) * J1 : (sK[fb][k1] * fy1) * J1; reskb = w * fc; }
-                } else {
-                    const double fy2 = in2 ? sh.b[r][k2][m2] : 0.0;
-                    const double J2 = sh.J[r][k2];
-                    if (doa) {
-                        const double v1 = plusa ? (sK[fa][k1] * (fy1 - fx)) * J1 : (sK[fa][k1] * fy1) * J1;
-                        const double v2 = plusa ? (sK[fa][k2] * (fy2 - fx)) * J2 : (sK[fa][k2] * fy2) * J2;
-                        const double fsum = v1 + v2;
-                        reska = reska + w * fsum;
-                    }
-                    if (dob) {
-                        const double v1 = plusb ? (sK[fb][k1] * (fy1 - fx)) * J1 : (sK[fb][k1] * fy1) * J1;
-                        const double v2 = plusb ? (sK[fb][k2] * (fy2 - fx)) * J2 : (sK[fb][k2] * fy2) * J2;
-                        const double fsum = v1 + v2;
-                        reskb = reskb + w * fsum;
-                    }
+        double reska = 0.0, reskb = 0.0;
+        for (int s = 0; s <= 10; s++) {
+            const int tt = (s == 0) ? 11 : ((s <= 5) ? 2 * s : 2 * (s - 5) - 1);
+            const int k1 = 21 * iv + ((s == 0) ? 0 : 2 * tt - 1);
+            const int k2 = k1 + 1;
+            const int m1 = j - sh.iS[r][k1];
+            const bool in1 = (m1 >= 0 && m1 < 6);
+            bool in2 = false;
+            int m2 = 0;
+            if (s != 0) { m2 = j - sh.iS[r][k2]; in2 = (m2 >= 0 && m2 < 6); }
+            const bool doa = plusa || in1 || in2, dob = plusb || in1 || in2;
+            if (!(doa || dob)) continue;
+            const double fy1 = in1 ? sh.b[r][k1][m1] : 0.0;
+            const double J1 = sh.J[r][k1];
+            const double w = c_wgk[tt];
+            if (s == 0) {
+                if (doa) { const double fc = plusa ? (sK[fa][k1] * (fy1 - fx)) * J1 : (sK[fa][k1] * fy1) * J1; reska = w * fc; }
+                if (dob) { const double fc = plusb ? (sK[fb][k1] * (fy1 - fx)) * J1 : (sK[fb][k1] * fy1) * J1; reskb = w * fc; }
+            } else {
+                const double fy2 = in2 ? sh.b[r][k2][m2] : 0.0;
+                const double J2 = sh.J[r][k2];
+                if (doa) {
+                    const double v1 = plusa ? (sK[fa][k1] * (fy1 - fx)) * J1 : (sK[fa][k1] * fy1) * J1;
+                    const double v2 = plusa ? (sK[fa][k2] * (fy2 - fx)) * J2 : (sK[fa][k2] * fy2) * J2;
+                    const double fsum = v1 + v2;
+                    reska = reska + w * fsum;
+                }
+                if (dob) {
+                    const double v1 = plusb ? (sK[fb][k1] * (fy1 - fx)) * J1 : (sK[fb][k1] * fy1) * J1;
+                    const double v2 = plusb ? (sK[fb][k2] * (fy2 - fx)) * J2 : (sK[fb][k2] * fy2) * J2;
+                    const double fsum = v1 + v2;
+                    reskb = reskb + w * fsum;
                 }
             }
-            inta = inta + reska * sh.hl[r][iv];
-            intb = intb + reskb * sh.hl[r][iv];
         }
-        const size_t base = ((size_t)ixi * n + (size_t)(i0 + r)) * n + (size_t)(j - 1);
-        P[(size_t)fa * fstride + base] = inta;
-        P[(size_t)fb * fstride + base] = intb;
+        double* park = &sh.H[r][1][0][0] + (size_t)(t * 2) * 6;      // [column, pair][a, b][interval], NKERN * NNODE doubles per row are free
+        park[iv] = reska;
+        park[6 + iv] = reskb;
     } else {
-        const int e2 = e - nspec;
+        const int e2 = e;
         const int r = e2 / n, j = e2 - r * n + 1;
         const bool dense = (sh.allfinite[r] == 0);
         const int iSx = sh.iSx[r];
@@ -430,6 +436,28 @@ assemble_fixed_kernel(int n, int nxi, const double* __restrict__ xi_arr, int gri
 #pragma unroll
         for (int f = 0; f < NKERN; f++) P[(size_t)f * fstride + rowbase + (size_t)(j - 1)] = integral[f];
     }
+    }
+    __syncthreads();
+    // second pass of the six heavy columns: integral = sum over the intervals of resk * hlgth, in the reference's order
+    for (int ep = tid; ep < nspec; ep += K1_THREADS) {
+        const int r = ep / (6 * NPAIR), t = ep - r * 6 * NPAIR;
+        if (sh.allfinite[r] == 0) continue;
+        const int jh = t / NPAIR, pr = t - NPAIR * jh;
+        if (sh.bx[r][jh] == 0.0) continue;
+        int fa = PA[0], fb = PB[0];
+#pragma unroll
+        for (int q = 1; q < NPAIR; q++)
+            if (q == pr) { fa = PA[q]; fb = PB[q]; }
+        const double* park = &sh.H[r][1][0][0] + (size_t)(t * 2) * 6;
+        double inta = 0.0, intb = 0.0;
+#pragma unroll
+        for (int iv = 0; iv < 6; iv++) {
+            inta = inta + park[iv] * sh.hl[r][iv];
+            intb = intb + park[6 + iv] * sh.hl[r][iv];
+        }
+        const size_t base = ((size_t)ixi * n + (size_t)(i0 + r)) * n + (size_t)(sh.iSx[r] + jh - 1);
+        P[(size_t)fa * fstride + base] = inta;
+        P[(size_t)fb * fstride + base] = intb;
     }
 
     __syncthreads();
